@@ -1,0 +1,104 @@
+"""The CPU oracle against the vectors produced by the reference's own Python
+(oracle/gen_golden.py; reference files src/ReadsCluster.py, src/DataScanner.py,
+src/DecisionMaker.py).  CPU only."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+
+def _load(path):
+    return np.load(path, allow_pickle=True)
+
+
+@pytest.mark.parametrize("name", ["em_a", "em_b", "em_c", "em_d", "em_e", "em_f"])
+def test_em_cluster_matches_reference(oracle, golden_dir, name):
+    g = _load(os.path.join(golden_dir, name + ".npz"))
+    X = g["X"]
+    out, info = oracle.em_cluster(X.copy(), reseed=True, return_info=True)
+    K, _, labels, theta, gamma, pie, bics = out
+    assert K == int(g["K"])
+    assert np.array_equal(labels, g["Rclust"])           # assignments: exact
+    np.testing.assert_allclose(bics, g["bics"], rtol=1e-9, atol=0)
+    np.testing.assert_allclose(gamma, g["gamma"], rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(pie, g["pie"], rtol=1e-12)
+    np.testing.assert_allclose(theta, g["theta"], rtol=1e-9, atol=1e-300)
+    np.testing.assert_array_equal(info["sim"], g["sim"])
+    # the Dirichlet fallback consumes the global RNG exactly like the reference
+    assert (info["n_fallback"] > 0) == (int(g["dirichlet_calls"]) > 0)
+
+
+WINDOWS = ["window_del", "window_ins", "window_nosv", "window_shallow", "window_lowerr",
+           "window_emptyreads"]
+
+
+@pytest.mark.parametrize("name", WINDOWS)
+def test_decision_matches_reference(oracle, golden_dir, name):
+    g = _load(os.path.join(golden_dir, name + ".npz"))
+    rec = oracle.decision(str(g["rec"]), list(g["seqs"]), np.array(g["ids"]), str(g["f5"]), str(g["f3"]))
+    assert [str(x) for x in rec] == list(g["record"])
+
+
+@pytest.mark.parametrize("name", [w for w in WINDOWS if w != "window_shallow"])
+def test_feature_selection_matches_reference(oracle, golden_dir, name):
+    g = _load(os.path.join(golden_dir, name + ".npz"))
+    enc, X, ids = oracle.msa_feature_selection(list(g["seqs"]), str(g["f5"]), str(g["f3"]), np.array(g["ids"]))
+    assert np.array_equal(enc, g["enc"])
+    assert np.array_equal(X, g["X"])
+    assert list(ids) == list(g["ids2"])
+    assert np.array_equal(oracle.call_margin(list(g["msa"])[0], str(g["f5"]), str(g["f3"])), g["margin"])
+    # SeqDecoder round trip (DataScanner.py:131-137): rows of the MSA de-gap to the inputs
+    seqs = [s for s in g["seqs"] if len(s) > 0]
+    for row, s in zip(enc[:len(seqs)], seqs):
+        assert oracle.decode_row(row) == s
+
+
+def test_poa_frozen_cases(oracle, golden_dir):
+    cases = json.load(open(os.path.join(golden_dir, "poa_cases.json")))["cases"]
+    for cs in cases:
+        s = oracle.PoaSession(1)
+        alns = [s.add(x).tolist() for x in cs["seqs"]]
+        assert alns == cs["alignments"]
+        assert s.consensus() == cs["consensus"]
+        msa = s.msa()
+        assert msa == cs["msa"]
+        g = s.graph()
+        assert g["rank_node"].tolist() == cs["rank_node"]
+        assert g["in_tail"].tolist() == cs["in_tail"]
+        assert g["in_weight"].tolist() == cs["in_weight"]
+        # size-independent properties: every row de-gaps to its input; equal widths
+        nonempty = [x for x in cs["seqs"] if x]
+        assert [r.replace("-", "") for r in msa] == nonempty
+        assert len({len(r) for r in msa}) <= 1
+        s.close()
+
+
+def test_poa_trivial_known_answers(oracle):
+    assert oracle.poa(["ACGT"], 1) == ("ACGT", ["ACGT"])
+    assert oracle.poa(["ACGT", "ACGT", "ACGT"], 1) == ("ACGT", ["ACGT"] * 3)
+    cons, msa = oracle.poa(["ACGTACGT", "ACGACGT"], 1)
+    assert msa == ["ACGTACGT", "ACG-ACGT"]
+    cons, msa = oracle.poa(["ACGTACGT", "ACGTTACGT", "ACGTTACGT"], 1)
+    assert cons == "ACGTTACGT"
+
+
+def test_levenshtein_known_answers(oracle, golden_dir):
+    cases = json.load(open(os.path.join(golden_dir, "lev_cases.json")))["cases"]
+    for a, b, d in cases:
+        assert oracle.levenshtein(a, b) == d
+        assert oracle.levenshtein(a, b, bitparallel=True) == d
+
+
+def test_levenshtein_bitparallel_equals_dp(oracle):
+    rng = np.random.default_rng(3)
+    for _ in range(150):
+        la, lb = int(rng.integers(0, 300)), int(rng.integers(0, 300))
+        a = "".join(rng.choice(list("ACGT"), la))
+        b = "".join(rng.choice(list("ACGT"), lb))
+        assert oracle.levenshtein(a, b, True) == oracle.levenshtein(a, b, False)
+    seqs = ["".join(rng.choice(list("ACGT"), int(rng.integers(1, 150)))) for _ in range(6)]
+    m = oracle.levenshtein_matrix(seqs)
+    assert np.array_equal(m, m.T) and (np.diag(m) == 0).all()
+    assert m[1, 4] == oracle.levenshtein(seqs[1], seqs[4])
