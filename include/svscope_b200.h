@@ -1,0 +1,132 @@
+/* svscope_b200 — C ABI of the B200-native localGraph hot path.
+ *
+ * The reference (negi2331026/SVScope) is pure Python and reaches its numeric kernels through
+ * Python imports, not an FFI.  Each entry point below names the reference interface it
+ * stands in for; the Python modules in svscope_b200/ bind them with ctypes and keep the
+ * reference's call signatures (INTEGRATION.md shows the binding a maintainer would add).
+ *
+ * Conventions: plain pointers and sizes, buffers owned by the caller, every function returns
+ * 0 on success or a negative error code; svs_last_error() gives the message of the last
+ * failure on that context.  Host pointers unless a parameter says "device".  A context is
+ * bound to one CUDA device; calls on one context must not overlap in time.
+ */
+#ifndef SVSCOPE_B200_H_
+#define SVSCOPE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct svs_ctx svs_ctx;
+typedef struct svs_reads svs_reads;
+typedef struct svs_poa_result svs_poa_result;
+
+enum {
+  SVS_OK = 0,
+  SVS_ERR_CUDA = -1,        /* CUDA runtime failure (message has the CUDA error string) */
+  SVS_ERR_ARG = -2,         /* invalid argument */
+  SVS_ERR_UNSUPPORTED = -3, /* e.g. scoring outside the supported convex-gap family */
+  SVS_ERR_CAPACITY = -4,    /* a single alignment does not fit the device arena */
+  SVS_ERR_INTERNAL = -5
+};
+
+/* ---- context -------------------------------------------------------------------------- */
+int svs_create(int device, svs_ctx** out);
+void svs_destroy(svs_ctx* ctx);
+const char* svs_last_error(const svs_ctx* ctx);
+const char* svs_version(void);
+/* Options (all optional): "poa_threads" CTA size of the alignment kernel (128|256|512),
+ * "ring_rows" packed rows kept in shared memory, "workers" host threads that own graphs and
+ * streams, "arena_mb" device scratch arena in MiB (0 = 70 % of free memory). */
+int svs_set_option(svs_ctx* ctx, const char* key, int64_t value);
+int64_t svs_get_option(const svs_ctx* ctx, const char* key);
+
+/* ---- read sets ------------------------------------------------------------------------ */
+/* Copies n_seqs sequences (concatenated, 1 byte per base, seq i = seqs[off[i]..off[i+1]))
+ * to device memory once, so that later calls start with the reads resident in HBM. */
+int svs_reads_upload(svs_ctx* ctx, const uint8_t* seqs, const int64_t* off, int64_t n_seqs,
+                     svs_reads** out);
+void svs_reads_free(svs_reads* reads);
+
+/* ---- partial-order alignment ----------------------------------------------------------
+ * Replaces `spoa.poa(sequences, algorithm, genmsa, m, n, g, e, q, c)` of pyspoa 0.2.1
+ * (reference call sites src/DataScanner.py:206,213 for the window MSA and
+ * src/DecisionMaker.py:160,171 for the per-cluster consensus), batched over n_groups
+ * independent sequence groups.  Group k consists of the sequences
+ * members[group_off[k] .. group_off[k+1]) (indices into the read set), aligned in that order.
+ * Only algorithm 1 (global) with convex gaps is on the hot path; other modes return
+ * SVS_ERR_UNSUPPORTED.  Empty sequences are skipped and get no MSA row, as in spoa. */
+int svs_poa_batch(svs_ctx* ctx, const svs_reads* reads, const int64_t* members,
+                  const int64_t* group_off, int64_t n_groups, int algorithm, int m, int n, int g,
+                  int e, int q, int c, int want_msa, svs_poa_result** out);
+/* per group: consensus length, MSA rows (non-empty sequences) and MSA columns */
+int svs_poa_result_sizes(const svs_poa_result* res, int64_t* cons_len, int64_t* msa_rows,
+                         int64_t* msa_cols);
+/* consensus strings concatenated in group order; MSA matrices (rows*cols chars, row-major)
+ * concatenated in group order.  Either pointer may be NULL. */
+int svs_poa_result_copy(const svs_poa_result* res, uint8_t* consensus, uint8_t* msa);
+/* stats[0] DP cells, [1] alignments, [2] sum of DP-kernel ms (events on the launch streams),
+ * [3] sum of traceback-kernel ms, [4] wall ms of the call, [5] launches of the DP kernel,
+ * [6] launches of the traceback kernel, [7] bytes host->device, [8] bytes device->host,
+ * [9] algorithmic bytes (read + graph + path), [10] exported rows,
+ * [11] graph rows total */
+int svs_poa_result_stats(const svs_poa_result* res, double* stats, int n_stats);
+void svs_poa_result_free(svs_poa_result* res);
+
+/* Debug/test entry: one alignment of `read` against the graph built from the previous
+ * sequences of a group, returning the alignment pairs (node id | -1, position | -1). */
+int svs_poa_align_pairs(svs_ctx* ctx, const uint8_t* seqs, const int64_t* off, int64_t n_seqs,
+                        int32_t* pair_node, int32_t* pair_pos, int64_t cap, int64_t* n_pairs,
+                        int64_t* seq_pair_off);
+
+/* ---- MSA post-processing ---------------------------------------------------------------
+ * Replaces SeqEncoder + the column statistics of FindNonSameSite (src/DataScanner.py:124-129,
+ * 167-179, 214-219), the ZeroParamNum count of EMCluster (src/ReadsCluster.py:226-234) and
+ * pariwiseDistance (src/ReadsCluster.py:44-59), batched over windows.  Window w has an
+ * encoded read matrix enc[w] of n_rows[w] x n_cols[w] symbols 0..4 (ref row excluded,
+ * row-major, concatenated), a column mask `drop` (1 = flank column to ignore) and a cutoff.
+ * Outputs per window: keep[col] = 1 for selected feature columns, nf, zero_params, and the
+ * n_rows x n_rows identity COUNTS over the selected columns (the caller divides by nf). */
+int svs_msa_features(svs_ctx* ctx, int64_t n_windows, const int8_t* enc, const int64_t* enc_off,
+                     const int32_t* n_rows, const int32_t* n_cols, const uint8_t* drop,
+                     const int64_t* col_off, const double* cutoff, uint8_t* keep, int32_t* nf,
+                     int32_t* zero_params, int32_t* ident, const int64_t* ident_off);
+
+/* ---- sequence mixture model -----------------------------------------------------------
+ * Replaces ReadsCluster.EM (src/ReadsCluster.py:190-209: pitheta_updating, gamma_updating and
+ * the final loglik) for n_tasks (window, K) pairs.  Task t works on X[t] (N x nf symbols
+ * 0..4, row-major int8 at x_off[t]) with K[t] components.  Start state: either hard labels
+ * (init_labels at lab_off[t], values 0..K-1; -1 offset means "use theta/pi start"), or
+ * theta (K x nf x 5) and pi (K) given in theta_io / pi_io.  Runs `n_steps` M+E iterations
+ * after the initial M,E (reference: 20).  Outputs: gamma (N x K), theta (K x nf x 5),
+ * pi (K), loglik (N), and status[t] = -1 if finished, else the index (0 = initial M-step)
+ * of the M-step at which some pi*N < 1 or NaN appeared (the reference then re-draws theta
+ * from numpy's global RNG, which stays on the host: the caller supplies the draw and
+ * resumes with start_step = status+... see svscope_b200/ReadsCluster.py). */
+int svs_em_batch(svs_ctx* ctx, int64_t n_tasks, const int8_t* X, const int64_t* x_off,
+                 const int32_t* N, const int32_t* nf, const int32_t* K, const int32_t* init_labels,
+                 const int64_t* lab_off, int32_t n_steps, const int32_t* start_step,
+                 double* gamma, const int64_t* gamma_off, double* theta_io, const int64_t* theta_off,
+                 double* pi_io, const int64_t* pi_off, double* loglik, const int64_t* lik_off,
+                 int32_t* status);
+
+/* ---- read-by-read edit distances -------------------------------------------------------
+ * Replaces the Levenshtein.distance matrix of the commented FindSomClust
+ * (src/DecisionMaker.py:76-84): for every group the full symmetric matrix of unit-cost edit
+ * distances between its member sequences (Myers/Hyyro bit-parallel, batched).
+ * dist holds, per group, n x n int32 row-major at dist_off[k]. */
+int svs_edit_distance_matrix(svs_ctx* ctx, const svs_reads* reads, const int64_t* members,
+                             const int64_t* group_off, int64_t n_groups, int32_t* dist,
+                             const int64_t* dist_off, double* stats, int n_stats);
+/* pairs form: distance of reads a[i] and b[i] */
+int svs_edit_distance_pairs(svs_ctx* ctx, const svs_reads* reads, const int64_t* a,
+                            const int64_t* b, int64_t n_pairs, int32_t* dist, double* stats,
+                            int n_stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVSCOPE_B200_H_ */

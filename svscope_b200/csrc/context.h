@@ -1,0 +1,59 @@
+// Library context: one CUDA device, options, error string, device scratch arena.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/svscope_b200.h"
+
+struct svs_ctx {
+  int device = 0;
+  std::string error;
+  // options
+  int poa_threads = 256;
+  int ring_rows = 12;
+  int workers = 4;
+  int64_t arena_mb = 0;
+  int tb_mode = 0;
+  // device arena shared by the batched calls (allocated lazily, reused)
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  int sm_count = 0;
+  std::mutex mu;
+};
+
+struct svs_reads {
+  svs_ctx* ctx = nullptr;
+  std::vector<uint8_t> host;     // concatenated sequences
+  std::vector<int64_t> off;      // n+1
+  uint8_t* dev = nullptr;        // device copy of `host`
+  int64_t n = 0;
+};
+
+namespace svs {
+
+inline int fail(svs_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->error = msg;
+  return code;
+}
+
+#define SVS_CUDA(ctx, expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t err__ = (expr);                                                              \
+    if (err__ != cudaSuccess) {                                                              \
+      char buf__[512];                                                                       \
+      std::snprintf(buf__, sizeof(buf__), "%s failed: %s (%s:%d)", #expr,                    \
+                    cudaGetErrorString(err__), __FILE__, __LINE__);                          \
+      return ::svs::fail((ctx), SVS_ERR_CUDA, buf__);                                        \
+    }                                                                                        \
+  } while (0)
+
+int ensure_arena(svs_ctx* ctx);
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace svs

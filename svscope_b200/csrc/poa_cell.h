@@ -1,0 +1,220 @@
+// Cell-level arithmetic of the sequence-to-graph alignment, shared by the CUDA kernels
+// (poa_kernels.cu) and by host code (column-0 codes in poa_graph.cpp, the CPU emulation used
+// by tests/).  Everything here is integer and exact.
+//
+// Recurrences (global alignment, two-piece "convex" gaps; behaviour of spoa's scalar engine,
+// SURVEY.md Appendix B) for row i (graph node) with predecessor rows p_0..p_{d-1} in stored
+// in-edge order, column j (read position j-1), substitution score s:
+//   F[i][j] = max_k max(H[p_k][j]+g, F[p_k][j]+e)      O[i][j] = max_k max(H[p_k][j]+q, O[p_k][j]+c)
+//   D[i][j] = max_k H[p_k][j-1] + s                    A[i][j] = max(D, F, O)
+//   E[i][j] = max(A[i][j-1]+g, E[i][j-1]+e)            Q[i][j] = max(A[i][j-1]+q, Q[i][j-1]+c)
+//   H[i][j] = max(A, E, Q)
+// E is opened from A instead of H.  H and Q are unchanged by that and every equality test
+// of the traceback has the same outcome (DESIGN.md "Row scan"): a gap of one piece opened
+// directly on top of a gap of the other piece never defines H, and in the one traceback test
+// where the E values themselves differ the Q alternative decides.  This turns the horizontal
+// dependency into two independent max-plus prefix scans.
+//
+// Instead of keeping five score matrices for an equality-test traceback, every cell emits a
+// 16-bit code holding exactly the decisions that traceback would take there:
+//   bits 0-1  move that defines H: 0 diagonal, 1 vertical, 2 horizontal
+//   bit  2    "extend" flag of a vertical / horizontal move (gap continues)
+//   bit  3    horizontal continuation: E[j]+e==E[j+1] || Q[j]+c==Q[j+1]
+//   bit  4    stop flag of the vertical-extension walk at this cell
+//   bits 5-9  in-edge index of the diagonal / vertical move
+//   bits 10-14 in-edge index of the vertical-extension walk (31 = none: go to the source row)
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define SVS_HD __host__ __device__ __forceinline__
+#else
+#define SVS_HD inline
+#endif
+
+namespace svs {
+
+constexpr int32_t kNeg = -(1 << 28);  // "minus infinity": |scores| stay below 2^26
+constexpr uint32_t kMoveDiag = 0, kMoveVert = 1, kMoveHorz = 2;
+constexpr uint32_t kNoPred = 31;
+constexpr uint32_t kMaxIndeg = 31;        // in-edge index must fit 5 bits, 31 is reserved
+constexpr int64_t kMaxScoreSpan = 1 << 26;
+constexpr uint8_t kFlagSink = 1, kFlagExport = 4;  // per-row flags of the ranked graph
+
+struct Scores {
+  int32_t m, n, g, e, q, c;
+};
+
+SVS_HD int32_t imax(int32_t a, int32_t b) { return a > b ? a : b; }
+SVS_HD int32_t imin(int32_t a, int32_t b) { return a < b ? a : b; }
+
+SVS_HD uint16_t make_code(uint32_t move, uint32_t ext, uint32_t lcnext, uint32_t upstop,
+                          uint32_t k_move, uint32_t k_up) {
+  return static_cast<uint16_t>(move | (ext << 2) | (lcnext << 3) | (upstop << 4) | (k_move << 5) |
+                               (k_up << 10));
+}
+
+// One word per cell carries all a successor row needs: H, and F and O as clamped distances
+// below H.  F matters to a successor only through max(H+g, F+e) and the equality tests
+// against it, i.e. only while H-F <= e-g (<= 2); likewise O while H-O <= c-q (<= 6).
+SVS_HD int32_t pack_cell(int32_t H, int32_t F, int32_t O) {
+  const int32_t dF = imin(H - F, 3);
+  const int32_t dO = imin(H - O, 7);
+  return H * 32 + dF * 8 + dO;
+}
+SVS_HD void unpack_cell(int32_t w, int32_t& H, int32_t& F, int32_t& O) {
+  H = w >> 5;
+  F = H - ((w >> 3) & 3);
+  O = H - (w & 7);
+}
+SVS_HD int32_t unpack_h(int32_t w) { return w >> 5; }
+
+// Source row (row 0): H[0][0]=0, H[0][j]=max(g+(j-1)e, q+(j-1)c); F, O = -inf for j>=1.
+SVS_HD int32_t row0_e(const Scores& s, int32_t j) { return j == 0 ? 0 : s.g + (j - 1) * s.e; }
+SVS_HD int32_t row0_q(const Scores& s, int32_t j) { return j == 0 ? 0 : s.q + (j - 1) * s.c; }
+SVS_HD int32_t row0_h(const Scores& s, int32_t j) {
+  return j == 0 ? 0 : imax(row0_e(s, j), row0_q(s, j));
+}
+
+// Running decisions of one cell over its predecessor rows.  `meta` packs the first in-edge
+// index attaining each maximum and the flags taken there:
+//   bits 0-4 kF, 5-9 kO, 10-14 kD, 15-19 kV, bit 20 sF (open H+g attains F), bit 21 sO (open
+//   H+q attains O), bit 22 xV (the vertical move at kV is a gap extension).
+struct CellAcc {
+  int32_t Fm, Om, D;  // maxima of the F, O and diagonal candidates; V = max(Fm, Om)
+  uint32_t meta;
+};
+
+// first predecessor (k = 0)
+SVS_HD void cell_pred0(CellAcc& a, int32_t Hp, int32_t Fp, int32_t Op, int32_t Hpl, int32_t sub,
+                       const Scores& s) {
+  const int32_t G = Hp + s.g, Fe = Fp + s.e, Oq = Hp + s.q, Oe = Op + s.c;
+  a.Fm = imax(G, Fe);
+  a.Om = imax(Oq, Oe);
+  a.D = Hpl + sub;
+  const int32_t V = imax(a.Fm, a.Om);
+  const uint32_t sF = G >= Fe, sO = Oq >= Oe;
+  const uint32_t xV = (Fe == V) || (G != V && Oe == V);
+  a.meta = (sF << 20) | (sO << 21) | (xV << 22);
+}
+
+// further predecessors (k >= 1): strict ">" keeps the first in-edge that attains a maximum
+SVS_HD void cell_predk(CellAcc& a, uint32_t k, int32_t Hp, int32_t Fp, int32_t Op, int32_t Hpl,
+                       int32_t sub, const Scores& s) {
+  const int32_t G = Hp + s.g, Fe = Fp + s.e, Oq = Hp + s.q, Oe = Op + s.c;
+  const int32_t Fc = imax(G, Fe), Oc = imax(Oq, Oe), Dk = Hpl + sub;
+  const int32_t Vk = imax(Fc, Oc);
+  const int32_t Vcur = imax(a.Fm, a.Om);
+  if (Vk > Vcur) {
+    const uint32_t xk = (Fe == Vk) || (G != Vk && Oe == Vk);
+    a.meta = (a.meta & ~((31u << 15) | (1u << 22))) | (k << 15) | (xk << 22);
+  }
+  if (Fc > a.Fm) {
+    a.Fm = Fc;
+    a.meta = (a.meta & ~(31u | (1u << 20))) | k | (static_cast<uint32_t>(G >= Fe) << 20);
+  }
+  if (Oc > a.Om) {
+    a.Om = Oc;
+    a.meta = (a.meta & ~((31u << 5) | (1u << 21))) | (k << 5) | (static_cast<uint32_t>(Oq >= Oe) << 21);
+  }
+  if (Dk > a.D) {
+    a.D = Dk;
+    a.meta = (a.meta & ~(31u << 10)) | (k << 10);
+  }
+}
+
+// State of the previous column of the same row.
+struct RowCarry {
+  int32_t A, E, Q, H;
+};
+
+// Completes a cell once the horizontal state of the previous column is known.
+SVS_HD uint16_t cell_finish(const CellAcc& a, RowCarry& cy, const Scores& s, int32_t& H_out) {
+  const int32_t E = imax(cy.A + s.g, cy.E + s.e);
+  const int32_t Q = imax(cy.A + s.q, cy.Q + s.c);
+  const int32_t V = imax(a.Fm, a.Om);
+  const int32_t A = imax(a.D, V);
+  const int32_t H = imax(A, imax(E, Q));
+  const uint32_t kF = a.meta & 31, kO = (a.meta >> 5) & 31;
+  uint32_t move, ext, km;
+  if (a.D == H) {
+    move = kMoveDiag; ext = 0; km = (a.meta >> 10) & 31;
+  } else if (V == H) {
+    move = kMoveVert; ext = (a.meta >> 22) & 1; km = (a.meta >> 15) & 31;
+  } else {
+    move = kMoveHorz; km = 0;
+    ext = (cy.E + s.e == H) || (cy.H + s.g != H && cy.Q + s.c == H);
+  }
+  const uint32_t lcnext = (E + s.e >= A + s.g) || (Q + s.c >= A + s.q);
+  const uint32_t ku = kF <= kO ? kF : kO;
+  const uint32_t stop = kF <= kO ? (a.meta >> 20) & 1 : (a.meta >> 21) & 1;
+  cy.A = A; cy.E = E; cy.Q = Q; cy.H = H;
+  H_out = H;
+  return make_code(move, ext, lcnext, stop, km, ku);
+}
+
+// Traceback code of a source-row cell (0, j), j >= 1: always a horizontal move.
+SVS_HD uint16_t row0_code(const Scores& s, int32_t j) {
+  const int32_t H = row0_h(s, j);
+  const int32_t El = row0_e(s, j - 1), Ql = row0_q(s, j - 1), Hl = row0_h(s, j - 1);
+  const uint32_t ext = (El + s.e == H) || (Hl + s.g != H && Ql + s.c == H);
+  const uint32_t lcnext = (row0_e(s, j) + s.e == row0_e(s, j + 1)) || (row0_q(s, j) + s.c == row0_q(s, j + 1));
+  return make_code(kMoveHorz, ext, lcnext, 0, 0, 0);
+}
+
+// Walks the stored decisions from (best_row, L) back to (0, 0) and writes the alignment
+// pairs (node id | -1, read position | -1) in REVERSE order.  Returns the number of pairs,
+// or -1 if `cap` pairs do not suffice.
+SVS_HD int32_t traceback_walk(uint32_t best_row, uint32_t L, const uint16_t* codes, uint64_t ldc,
+                              const uint16_t* col0code, const uint32_t* pred_off,
+                              const uint32_t* preds, const uint32_t* node_id, const Scores& s,
+                              int32_t* out_pairs, int32_t cap) {
+  uint32_t i = best_row, j = L;
+  int32_t n = 0;
+  auto code_at = [&](uint32_t ii, uint32_t jj) -> uint32_t {
+    if (ii == 0) return jj == 0 ? 0u : row0_code(s, static_cast<int32_t>(jj));
+    if (jj == 0) return col0code[ii];
+    return codes[static_cast<uint64_t>(ii - 1) * ldc + (jj - 1)];
+  };
+  auto pred_row = [&](uint32_t ii, uint32_t k) -> uint32_t {
+    return k == kNoPred ? 0u : preds[pred_off[ii] + k];
+  };
+  while (!(i == 0 && j == 0)) {
+    const uint32_t cd = code_at(i, j);
+    const uint32_t move = cd & 3, ext = (cd >> 2) & 1, km = (cd >> 5) & 31;
+    uint32_t pi, pj;
+    if (move == kMoveDiag) { pi = pred_row(i, km); pj = j - 1; }
+    else if (move == kMoveVert) { pi = pred_row(i, km); pj = j; }
+    else { pi = i; pj = j - 1; }
+    if (n >= cap) return -1;
+    out_pairs[2 * n] = (i == pi) ? -1 : static_cast<int32_t>(node_id[i]);
+    out_pairs[2 * n + 1] = (j == pj) ? -1 : static_cast<int32_t>(j - 1);
+    ++n;
+    i = pi; j = pj;
+    if (move == kMoveHorz && ext) {
+      while (true) {
+        if (n >= cap) return -1;
+        out_pairs[2 * n] = -1;
+        out_pairs[2 * n + 1] = static_cast<int32_t>(j - 1);
+        ++n;
+        --j;
+        if (j == 0 || !((code_at(i, j) >> 3) & 1)) break;
+      }
+    } else if (move == kMoveVert && ext) {
+      while (i != 0) {
+        const uint32_t c2 = code_at(i, j);
+        const uint32_t stop = (c2 >> 4) & 1, ku = (c2 >> 10) & 31;
+        const uint32_t up = pred_row(i, ku);
+        if (n >= cap) return -1;
+        out_pairs[2 * n] = static_cast<int32_t>(node_id[i]);
+        out_pairs[2 * n + 1] = -1;
+        ++n;
+        i = up;
+        if (stop || i == 0) break;
+      }
+    }
+  }
+  return n;
+}
+
+}  // namespace svs

@@ -1,0 +1,376 @@
+// Sequence-to-graph alignment kernels for sm_100a (replace the dynamic programme and the
+// traceback inside `spoa.poa(sequences, 1)`; reference call sites src/DataScanner.py:206,213
+// and src/DecisionMaker.py:160,171).
+//
+// poa_dp_kernel   one CTA per (graph, read) alignment.  Rows (graph nodes in rank order) are
+//                 swept top to bottom; the T threads of the CTA own 8 consecutive read
+//                 columns each, so one pass covers a strip of 8*T columns and longer reads
+//                 take several passes that hand the strip boundary (H, A, E, Q per row)
+//                 through global memory.  Per row:
+//                   phase 1  every thread folds the predecessor rows into its 8 cells
+//                            (vertical / diagonal candidates, first-in-edge argmax);
+//                   scan     the horizontal gap states E, Q are two max-plus prefix scans:
+//                            8 cells in registers, warp shuffles, one shared-memory hop
+//                            across warps, ONE __syncthreads per row;
+//                   phase 2  H and the 16-bit traceback code of each cell; codes go to
+//                            global memory (16 B per thread, coalesced), the packed row to
+//                            the shared-memory ring and, if a far successor needs it, to
+//                            global memory.
+//                 Predecessor rows come from registers (rank-adjacent row), the ring of
+//                 the last `ring_rows` packed rows in shared memory, or the exported rows.
+// poa_tb_kernel   one thread per alignment walks the stored codes back to the origin.
+//
+// Integer arithmetic only; no tensor cores (nothing here is a dense contraction).
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "poa_cell.h"
+#include "poa_kernels.h"
+#include "poa_task.h"
+
+namespace svs {
+
+namespace {
+
+constexpr int kC = 8;            // columns per thread
+constexpr int kRowBatch = 32;    // rows whose metadata is staged in shared memory at once
+constexpr int kPredCap = kRowBatch * 32;
+constexpr int32_t kSrcRow0 = -1;
+constexpr int32_t kSrcAdj = -2;
+constexpr int32_t kSrcGlobal = 1 << 30;
+
+struct WarpPub {  // what the last lanes of a warp publish for the warp to its right
+  int32_t e31, e30, eloc7, q31, q30, qloc7, a7, pad;
+};
+
+struct Stage {
+  uint32_t poff[kRowBatch + 1];
+  int32_t psrc[kPredCap];
+  int32_t pbh[kPredCap];
+  int32_t xslot[kRowBatch];
+  int32_t bA[kRowBatch], bE[kRowBatch], bQ[kRowBatch];
+  uint8_t letter[kRowBatch];
+  uint8_t flags[kRowBatch];
+};
+
+template <int T>
+__global__ void __launch_bounds__(T, 512 / T) poa_dp_kernel(const PoaTask* __restrict__ tasks, const Scores s,
+                                                   const int ring_rows) {
+  constexpr int NW = T / 32;
+  constexpr int WC = T * kC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t* ring = reinterpret_cast<int32_t*>(smem_raw);
+  WarpPub* pub = reinterpret_cast<WarpPub*>(ring + static_cast<size_t>(ring_rows) * WC);
+  Stage& st = *reinterpret_cast<Stage*>(pub + 2 * NW);
+
+  const PoaTask tk = tasks[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t R = tk.R, L = tk.L;
+  const uint64_t bstride = static_cast<uint64_t>(R) + 1;
+
+  int32_t best = INT32_MIN;
+  uint32_t best_row = 0;
+
+  for (uint32_t pass = 0; pass < tk.npass; ++pass) {
+    const uint32_t jb = 1 + pass * tk.strip;
+    const uint32_t je = min(L, jb + tk.strip - 1);
+    const uint32_t j0 = jb + kC * tid;
+    const bool active = j0 <= je;
+    const bool last_pass = (pass + 1 == tk.npass);
+    const bool owns_end = last_pass && active && (L < j0 + kC);
+    const int c_end = owns_end ? static_cast<int>(L - j0) : -1;
+    const bool writes_bnd = !last_pass && (static_cast<uint32_t>(tid) == (je - jb) / kC);
+    const int32_t* bin = tk.bnd + static_cast<uint64_t>(pass & 1) * 4 * bstride;
+    int32_t* bout = tk.bnd + static_cast<uint64_t>((pass + 1) & 1) * 4 * bstride;
+
+    int32_t rd[kC];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) {
+      const uint32_t j = j0 + c;
+      rd[c] = (active && j <= L) ? static_cast<int32_t>(tk.read[j - 1]) : 0x100;
+    }
+    int32_t wprev[kC];       // packed cells of the previous row in my columns
+    int32_t hleft_adj = 0;   // H[i-1][j0-1]
+#pragma unroll
+    for (int c = 0; c < kC; ++c) wprev[c] = 0;
+
+    uint32_t slot = 1 % ring_rows;
+    for (uint32_t i0 = 1; i0 <= R; i0 += kRowBatch) {
+      const uint32_t nrows = min(static_cast<uint32_t>(kRowBatch), R - i0 + 1);
+      __syncthreads();
+      if (static_cast<uint32_t>(tid) < nrows) {
+        const uint32_t i = i0 + tid;
+        st.letter[tid] = tk.letter[i];
+        st.flags[tid] = tk.flags[i];
+        st.xslot[tid] = tk.xslot[i];
+        if (pass == 0) {
+          st.bA[tid] = tk.h0[i];
+          st.bE[tid] = kNeg;
+          st.bQ[tid] = kNeg;
+        } else {
+          st.bA[tid] = __ldcg(bin + bstride + i);
+          st.bE[tid] = __ldcg(bin + 2 * bstride + i);
+          st.bQ[tid] = __ldcg(bin + 3 * bstride + i);
+        }
+        const uint32_t base = tk.pred_off[i0];
+        const uint32_t pb = tk.pred_off[i], pe = tk.pred_off[i + 1];
+        st.poff[tid] = pb - base;
+        if (static_cast<uint32_t>(tid) == nrows - 1) st.poff[nrows] = pe - base;
+        for (uint32_t e = pb; e < pe; ++e) {
+          const uint32_t p = tk.preds[e];
+          int32_t src, bh;
+          if (p == 0) {
+            src = kSrcRow0;
+            bh = row0_h(s, static_cast<int32_t>(jb) - 1);
+          } else {
+            bh = (pass == 0) ? tk.h0[p] : __ldcg(bin + p);
+            if (p + 1 == i) src = kSrcAdj;
+            else if (i - p <= static_cast<uint32_t>(ring_rows)) src = static_cast<int32_t>(p % ring_rows);
+            else src = kSrcGlobal | tk.xslot[p];
+          }
+          st.psrc[e - base] = src;
+          st.pbh[e - base] = bh;
+        }
+      }
+      __syncthreads();
+
+      for (uint32_t r = 0; r < nrows; ++r) {
+        const uint32_t i = i0 + r;
+        const uint32_t nb = st.poff[r], ne = st.poff[r + 1];
+        const int32_t letter = st.letter[r];
+        CellAcc acc[kC];
+#pragma unroll
+        for (int c = 0; c < kC; ++c) { acc[c].Fm = 0; acc[c].Om = 0; acc[c].D = 0; acc[c].meta = 0; }
+
+        // ---- phase 1: fold predecessor rows ------------------------------------------
+        if (active) {
+          for (uint32_t e = nb; e < ne; ++e) {
+            const int32_t src = st.psrc[e];
+            int32_t w[kC];
+            int32_t hl;
+            if (src == kSrcAdj) {
+#pragma unroll
+              for (int c = 0; c < kC; ++c) w[c] = wprev[c];
+              hl = hleft_adj;
+            } else if (src == kSrcRow0) {
+#pragma unroll
+              for (int c = 0; c < kC; ++c) w[c] = pack_cell(row0_h(s, static_cast<int32_t>(j0) + c), kNeg, kNeg);
+              hl = row0_h(s, static_cast<int32_t>(j0) - 1);
+            } else if (src & kSrcGlobal) {
+              const int32_t* row = tk.xrows + static_cast<uint64_t>(src & ~kSrcGlobal) * tk.ldx + 3;
+              const int4 v0 = __ldcg(reinterpret_cast<const int4*>(row + j0));
+              const int4 v1 = __ldcg(reinterpret_cast<const int4*>(row + j0 + 4));
+              hl = unpack_h(__ldcg(row + j0 - 1));
+              w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
+              w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+            } else {
+              const int32_t* row = ring + static_cast<size_t>(src) * WC;
+              const int4 v0 = *reinterpret_cast<const int4*>(row + kC * tid);
+              const int4 v1 = *reinterpret_cast<const int4*>(row + kC * tid + 4);
+              hl = (tid == 0) ? st.pbh[e] : unpack_h(row[kC * tid - 1]);
+              w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
+              w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+            }
+            if (e == nb) {
+#pragma unroll
+              for (int c = 0; c < kC; ++c) {
+                int32_t Hp, Fp, Op;
+                unpack_cell(w[c], Hp, Fp, Op);
+                cell_pred0(acc[c], Hp, Fp, Op, hl, (letter == rd[c]) ? s.m : s.n, s);
+                hl = Hp;
+              }
+            } else {
+              const uint32_t k = e - nb;
+#pragma unroll
+              for (int c = 0; c < kC; ++c) {
+                int32_t Hp, Fp, Op;
+                unpack_cell(w[c], Hp, Fp, Op);
+                cell_predk(acc[c], k, Hp, Fp, Op, hl, (letter == rd[c]) ? s.m : s.n, s);
+                hl = Hp;
+              }
+            }
+          }
+        }
+
+        // ---- scan: horizontal gap states across the row ----------------------------------
+        int32_t a7 = 0;
+        int32_t el = kNeg, ql = kNeg, eloc7 = kNeg, qloc7 = kNeg;
+#pragma unroll
+        for (int c = 0; c < kC; ++c) {
+          const int32_t A = imax(acc[c].D, imax(acc[c].Fm, acc[c].Om));
+          if (c == kC - 1) { eloc7 = el; qloc7 = ql; a7 = A; }
+          el = imax(A + s.g, el + s.e);
+          ql = imax(A + s.q, ql + s.c);
+        }
+        const int32_t bA = st.bA[r], bE = st.bE[r], bQ = st.bQ[r];
+        int32_t ein0 = 0, qin0 = 0;
+        if (tid == 0) {  // the strip boundary enters through thread 0
+          ein0 = imax(bA + s.g, bE + s.e);
+          qin0 = imax(bA + s.q, bQ + s.c);
+          el = imax(el, ein0 + kC * s.e);
+          ql = imax(ql, qin0 + kC * s.c);
+        }
+        int32_t ve = el, vq = ql;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int32_t oe = __shfl_up_sync(0xffffffffu, ve, d);
+          const int32_t oq = __shfl_up_sync(0xffffffffu, vq, d);
+          if (lane >= d) {
+            ve = imax(ve, oe + kC * s.e * d);
+            vq = imax(vq, oq + kC * s.c * d);
+          }
+        }
+        const int par = static_cast<int>(i & 1);
+        {
+          const int32_t e30 = __shfl_sync(0xffffffffu, ve, 30);
+          const int32_t q30 = __shfl_sync(0xffffffffu, vq, 30);
+          if (lane == 31) {
+            WarpPub pb;
+            pb.e31 = ve; pb.e30 = e30; pb.eloc7 = eloc7;
+            pb.q31 = vq; pb.q30 = q30; pb.qloc7 = qloc7;
+            pb.a7 = a7; pb.pad = 0;
+            pub[par * NW + warp] = pb;
+          }
+        }
+        __syncthreads();
+        int32_t t1e = kNeg, t1q = kNeg, t2e = kNeg, t2q = kNeg;
+        if (warp > 0) {
+          if (lane < warp) {
+            const WarpPub pb = pub[par * NW + lane];
+            const int d1 = warp - 1 - lane;
+            t1e = pb.e31 + 32 * kC * s.e * d1;
+            t1q = pb.q31 + 32 * kC * s.c * d1;
+            if (lane < warp - 1) {
+              t2e = pb.e31 + 32 * kC * s.e * (d1 - 1);
+              t2q = pb.q31 + 32 * kC * s.c * (d1 - 1);
+            }
+          }
+          t1e = __reduce_max_sync(0xffffffffu, t1e);
+          t1q = __reduce_max_sync(0xffffffffu, t1q);
+          t2e = __reduce_max_sync(0xffffffffu, t2e);
+          t2q = __reduce_max_sync(0xffffffffu, t2q);
+        }
+        const int32_t vte = imax(ve, t1e + kC * s.e * (lane + 1));
+        const int32_t vtq = imax(vq, t1q + kC * s.c * (lane + 1));
+        int32_t ein = __shfl_up_sync(0xffffffffu, vte, 1);
+        int32_t qin = __shfl_up_sync(0xffffffffu, vtq, 1);
+        if (lane == 0) { ein = t1e; qin = t1q; }
+        if (tid == 0) { ein = ein0; qin = qin0; }
+        const int32_t se = imax(ein + (kC - 1) * s.e, eloc7);  // E, Q at my last column
+        const int32_t sq = imax(qin + (kC - 1) * s.c, qloc7);
+        RowCarry cy;
+        cy.A = __shfl_up_sync(0xffffffffu, a7, 1);
+        cy.E = __shfl_up_sync(0xffffffffu, se, 1);
+        cy.Q = __shfl_up_sync(0xffffffffu, sq, 1);
+        if (lane == 0) {
+          if (warp == 0) {
+            cy.A = bA; cy.E = bE; cy.Q = bQ;
+          } else {
+            const WarpPub pb = pub[par * NW + warp - 1];
+            const int32_t einl = imax(pb.e30, t2e + kC * s.e * 31);
+            const int32_t qinl = imax(pb.q30, t2q + kC * s.c * 31);
+            cy.A = pb.a7;
+            cy.E = imax(einl + (kC - 1) * s.e, pb.eloc7);
+            cy.Q = imax(qinl + (kC - 1) * s.c, pb.qloc7);
+          }
+        }
+        cy.H = imax(cy.A, imax(cy.E, cy.Q));
+        hleft_adj = cy.H;
+
+        // ---- phase 2: H, traceback codes, packed row --------------------------------------
+        uint32_t cw[kC / 2];
+        int32_t hsel = INT32_MIN;
+#pragma unroll
+        for (int c = 0; c < kC; ++c) {
+          int32_t H;
+          const uint32_t cd = cell_finish(acc[c], cy, s, H);
+          wprev[c] = pack_cell(H, acc[c].Fm, acc[c].Om);
+          if (c & 1) cw[c >> 1] |= cd << 16; else cw[c >> 1] = cd;
+          if (c == c_end) hsel = H;
+        }
+        if (active) {
+          *reinterpret_cast<uint4*>(tk.codes + static_cast<uint64_t>(i - 1) * tk.ldc + (j0 - 1)) =
+              make_uint4(cw[0], cw[1], cw[2], cw[3]);
+          int32_t* rrow = ring + static_cast<size_t>(slot) * WC + kC * tid;
+          *reinterpret_cast<int4*>(rrow) = make_int4(wprev[0], wprev[1], wprev[2], wprev[3]);
+          *reinterpret_cast<int4*>(rrow + 4) = make_int4(wprev[4], wprev[5], wprev[6], wprev[7]);
+          if (st.flags[r] & kFlagExport) {
+            int32_t* xrow = tk.xrows + static_cast<uint64_t>(st.xslot[r]) * tk.ldx + 3;
+            *reinterpret_cast<int4*>(xrow + j0) = make_int4(wprev[0], wprev[1], wprev[2], wprev[3]);
+            *reinterpret_cast<int4*>(xrow + j0 + 4) = make_int4(wprev[4], wprev[5], wprev[6], wprev[7]);
+            if (tid == 0 && pass == 0) xrow[0] = pack_cell(bA, kNeg, kNeg);
+          }
+          if (writes_bnd) {
+            bout[i] = cy.H;
+            bout[bstride + i] = cy.A;
+            bout[2 * bstride + i] = cy.E;
+            bout[3 * bstride + i] = cy.Q;
+          }
+          if (owns_end && (st.flags[r] & kFlagSink) && hsel > best) {
+            best = hsel;
+            best_row = i;
+          }
+        }
+        slot = (slot + 1 == static_cast<uint32_t>(ring_rows)) ? 0 : slot + 1;
+      }
+    }
+    if (owns_end) {
+      tk.result[0] = static_cast<int32_t>(best_row);
+      tk.result[1] = best;
+      tk.result[3] = 0;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void poa_tb_kernel(const PoaTask* __restrict__ tasks, const Scores s, const int n_tasks) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_tasks) return;
+  const PoaTask tk = tasks[idx];
+  const int32_t n = traceback_walk(static_cast<uint32_t>(tk.result[0]), tk.L, tk.codes, tk.ldc,
+                                   tk.col0code, tk.pred_off, tk.preds, tk.node_id, s, tk.path,
+                                   static_cast<int32_t>(tk.path_cap));
+  tk.result[2] = n;
+}
+
+}  // namespace
+
+size_t poa_dp_smem_bytes(int threads, int ring_rows) {
+  return static_cast<size_t>(ring_rows) * threads * kC * sizeof(int32_t) +
+         2 * (threads / 32) * sizeof(WarpPub) + sizeof(Stage);
+}
+
+int poa_dp_cols_per_pass(int threads) { return threads * kC; }
+
+cudaError_t poa_dp_configure(int threads, int ring_rows) {
+  const int bytes = static_cast<int>(poa_dp_smem_bytes(threads, ring_rows));
+  switch (threads) {
+    case 128: return cudaFuncSetAttribute(poa_dp_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    case 256: return cudaFuncSetAttribute(poa_dp_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    case 512: return cudaFuncSetAttribute(poa_dp_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t poa_dp_launch(const PoaTask* d_tasks, int n_tasks, const Scores& s, int threads,
+                          int ring_rows, cudaStream_t stream) {
+  if (n_tasks <= 0) return cudaSuccess;
+  const size_t smem = poa_dp_smem_bytes(threads, ring_rows);
+  switch (threads) {
+    case 128: poa_dp_kernel<128><<<n_tasks, 128, smem, stream>>>(d_tasks, s, ring_rows); break;
+    case 256: poa_dp_kernel<256><<<n_tasks, 256, smem, stream>>>(d_tasks, s, ring_rows); break;
+    case 512: poa_dp_kernel<512><<<n_tasks, 512, smem, stream>>>(d_tasks, s, ring_rows); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t poa_tb_launch(const PoaTask* d_tasks, int n_tasks, const Scores& s, cudaStream_t stream) {
+  if (n_tasks <= 0) return cudaSuccess;
+  const int block = 32;
+  poa_tb_kernel<<<(n_tasks + block - 1) / block, block, 0, stream>>>(d_tasks, s, n_tasks);
+  return cudaGetLastError();
+}
+
+}  // namespace svs

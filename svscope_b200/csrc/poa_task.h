@@ -1,0 +1,35 @@
+// Device-visible descriptor of one (graph, read) alignment.  All pointers are device
+// pointers into the batch arena; the layout of the rank-ordered graph arrays is the one
+// produced by PoaGraph::export_ranked (poa_graph.h).
+#pragma once
+#include <cstdint>
+
+namespace svs {
+
+struct PoaTask {
+  // graph in rank order: row r = rank r-1, row 0 = virtual source row
+  const uint8_t* letter;      // [R+1]
+  const uint32_t* pred_off;   // [R+2]
+  const uint32_t* preds;      // predecessor rows in stored in-edge order (0 = source row)
+  const uint8_t* flags;       // [R+1] kFlagSink | kFlagExport
+  const int32_t* xslot;       // [R+1] slot of the row in `xrows`, or -1
+  const int32_t* h0;          // [R+1] H[row][0]
+  const uint16_t* col0code;   // [R+1] traceback codes of column 0
+  const uint32_t* node_id;    // [R+1]
+  const uint8_t* read;        // [L]
+  uint32_t R, L;
+  uint32_t strip, npass;      // columns per pass (multiple of 8), number of passes
+  // scratch
+  uint16_t* codes;            // [R][ldc] traceback codes of columns 1..L
+  uint64_t ldc;
+  int32_t* xrows;             // [n_export][ldx] packed cells of exported rows, column j at 3+j
+  uint64_t ldx;
+  int32_t* bnd;               // [2][4][R+1] strip boundary state (H, A, E, Q), ping-pong
+  // results
+  int32_t* result;            // [4] best_row, best_score, n_pairs, status
+  int32_t* path;              // [2*path_cap] alignment pairs in reverse order
+  uint32_t path_cap;
+  uint32_t pad_;
+};
+
+}  // namespace svs

@@ -1,0 +1,81 @@
+"""ctypes wrapper for the CPU emulation of the GPU alignment path (test infrastructure)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+LIB = os.path.join(HERE, "_build", "libpoa_emul.so")
+_lib = None
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, "poa_emul.cpp"), os.path.join(ROOT, "svscope_b200", "csrc", "poa_graph.cpp")]
+    deps = srcs + [os.path.join(ROOT, "svscope_b200", "csrc", h) for h in ("poa_cell.h", "poa_graph.h")]
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w"] + srcs + ["-o", LIB], check=True)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = ctypes.CDLL(build())
+        L.emu_new.restype = ctypes.c_void_p
+        L.emu_new.argtypes = [ctypes.c_int]
+        L.emu_free.argtypes = [ctypes.c_void_p]
+        L.emu_add.restype = ctypes.c_int64
+        L.emu_add.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]
+        L.emu_last_alignment.restype = ctypes.c_int64
+        L.emu_last_alignment.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+        L.emu_num_nodes.restype = ctypes.c_int64
+        L.emu_num_nodes.argtypes = [ctypes.c_void_p]
+        L.emu_rank_to_node.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.emu_consensus.restype = ctypes.c_int64
+        L.emu_consensus.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+        L.emu_msa_dims.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.emu_msa.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        _lib = L
+    return _lib
+
+
+class EmuSession:
+    def __init__(self, ring_rows=4):
+        self.h = lib().emu_new(ring_rows)
+
+    def add(self, seq):
+        b = seq.encode()
+        n = lib().emu_add(self.h, b, len(b))
+        nodes = np.empty(n, np.int32)
+        pos = np.empty(n, np.int32)
+        lib().emu_last_alignment(self.h, nodes.ctypes.data, pos.ctypes.data, n)
+        return np.stack([nodes, pos], axis=1)
+
+    def rank_to_node(self):
+        n = lib().emu_num_nodes(self.h)
+        out = np.empty(n, np.int32)
+        lib().emu_rank_to_node(self.h, out.ctypes.data)
+        return out
+
+    def consensus(self):
+        cap = lib().emu_num_nodes(self.h) + 1
+        buf = ctypes.create_string_buffer(cap)
+        n = lib().emu_consensus(self.h, buf, cap)
+        return buf.raw[:n].decode()
+
+    def msa(self):
+        r, c = ctypes.c_int64(), ctypes.c_int64()
+        lib().emu_msa_dims(self.h, ctypes.byref(r), ctypes.byref(c))
+        if r.value == 0 or c.value == 0:
+            return ["" for _ in range(r.value)]
+        buf = ctypes.create_string_buffer(r.value * c.value)
+        lib().emu_msa(self.h, buf)
+        return [buf.raw[i * c.value:(i + 1) * c.value].decode() for i in range(r.value)]
+
+    def close(self):
+        if self.h:
+            lib().emu_free(self.h)
+            self.h = None
