@@ -97,21 +97,23 @@ int svs_msa_features(svs_ctx* ctx, int64_t n_windows, const int8_t* enc, const i
 
 /* ---- sequence mixture model -----------------------------------------------------------
  * Replaces ReadsCluster.EM (src/ReadsCluster.py:190-209: pitheta_updating, gamma_updating and
- * the final loglik) for n_tasks (window, K) pairs.  Task t works on X[t] (N x nf symbols
- * 0..4, row-major int8 at x_off[t]) with K[t] components.  Start state: either hard labels
- * (init_labels at lab_off[t], values 0..K-1; -1 offset means "use theta/pi start"), or
- * theta (K x nf x 5) and pi (K) given in theta_io / pi_io.  Runs `n_steps` M+E iterations
- * after the initial M,E (reference: 20).  Outputs: gamma (N x K), theta (K x nf x 5),
- * pi (K), loglik (N), and status[t] = -1 if finished, else the index (0 = initial M-step)
- * of the M-step at which some pi*N < 1 or NaN appeared (the reference then re-draws theta
- * from numpy's global RNG, which stays on the host: the caller supplies the draw and
- * resumes with start_step = status+... see svscope_b200/ReadsCluster.py). */
+ * the log-likelihood of the last iteration) for n_tasks (window, K) pairs.  Task t works on
+ * X (N[t] x nf[t] symbols 0..4, row-major int8 at x_off[t]; tasks of one window may share it)
+ * with K[t] components (1..9).  Start state: hard labels 0..K-1 (init_labels at lab_off[t]),
+ * or, when lab_off[t] < 0, theta (K x nf x 5 at theta_off[t]) and pi (K at pi_off[t]).
+ * Schedule: [M from labels] E, then n_steps[t] (or n_steps_default when n_steps is NULL)
+ * times (M, E); the reference uses 20.  Outputs: gamma (N x K), pi (K), per-read
+ * log-likelihood (N), theta (only if want_theta) and status[t]: -1 when finished, else the
+ * index it (0 = the initial M-step) of the M-step in which some pi*N < 1 or NaN appeared.
+ * The reference then re-draws theta from numpy's global RNG (ReadsCluster.py:185-187); that
+ * draw stays on the host: the caller supplies theta, uniform pi, lab_off = -1 and
+ * n_steps - it remaining steps (svscope_b200/ReadsCluster.py does this). */
 int svs_em_batch(svs_ctx* ctx, int64_t n_tasks, const int8_t* X, const int64_t* x_off,
                  const int32_t* N, const int32_t* nf, const int32_t* K, const int32_t* init_labels,
-                 const int64_t* lab_off, int32_t n_steps, const int32_t* start_step,
-                 double* gamma, const int64_t* gamma_off, double* theta_io, const int64_t* theta_off,
-                 double* pi_io, const int64_t* pi_off, double* loglik, const int64_t* lik_off,
-                 int32_t* status);
+                 const int64_t* lab_off, int32_t n_steps_default, const int32_t* n_steps,
+                 int32_t want_theta, double* gamma, const int64_t* gamma_off, double* theta_io,
+                 const int64_t* theta_off, double* pi_io, const int64_t* pi_off, double* loglik,
+                 const int64_t* lik_off, int32_t* status);
 
 /* ---- read-by-read edit distances -------------------------------------------------------
  * Replaces the Levenshtein.distance matrix of the commented FindSomClust

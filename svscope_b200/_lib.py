@@ -36,7 +36,7 @@ SYMBOLS = {
     "svs_poa_result_free": (None, [c_vp]),
     "svs_poa_align_pairs": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int64, c_vp, c_vp, ctypes.c_int64, c_vp, c_vp]),
     "svs_msa_features": (ctypes.c_int, [c_vp, ctypes.c_int64] + [c_vp] * 12),
-    "svs_em_batch": (ctypes.c_int, [c_vp, ctypes.c_int64] + [c_vp] * 7 + [ctypes.c_int32, c_vp] + [c_vp] * 9),
+    "svs_em_batch": (ctypes.c_int, [c_vp, ctypes.c_int64] + [c_vp] * 7 + [ctypes.c_int32, c_vp, ctypes.c_int32] + [c_vp] * 9),
     "svs_edit_distance_matrix": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, c_vp, c_vp, c_vp, ctypes.c_int]),
     "svs_edit_distance_pairs": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, c_vp, c_vp, ctypes.c_int]),
 }

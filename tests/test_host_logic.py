@@ -1,0 +1,119 @@
+"""Host-side logic of the product on CPU: rank-order graph + cell arithmetic (through the
+sequential emulation of the kernels), flank columns, sharding, world_size-2 gather (gloo)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from svscope_b200 import batch, shard, synth
+
+
+def _random_group(rng, it):
+    L = int(rng.integers(1, 220))
+    n = int(rng.integers(2, 9))
+    base = synth._rand_seq(rng, L)
+    if it % 3 == 0:
+        mot = synth._rand_seq(rng, int(rng.integers(1, 6)))
+        base = np.tile(mot, max(1, L // len(mot)))
+    seqs = []
+    for _ in range(n):
+        s = base.copy()
+        for _ in range(int(rng.integers(0, 3))):
+            p = int(rng.integers(0, len(s) + 1))
+            ln = int(rng.integers(1, 40))
+            s = np.concatenate([s[:p], s[p + ln:]]) if rng.random() < 0.5 else \
+                np.concatenate([s[:p], synth._rand_seq(rng, ln), s[p:]])
+        if len(s) == 0:
+            s = synth._rand_seq(rng, 3)
+        seqs.append(synth._to_str(synth.noisy_copy(rng, s, float(rng.choice([0, 0.05, 0.15, 0.3])))))
+    if it % 7 == 0:
+        seqs[int(rng.integers(1, n))] = ""
+    return seqs
+
+
+def test_emulated_kernel_path_equals_oracle(oracle):
+    """Product host graph + packed-cell arithmetic + code walker == five-matrix oracle."""
+    from tests.emul.emul import EmuSession
+    rng = np.random.default_rng(11)
+    for it in range(120):
+        seqs = _random_group(rng, it)
+        o, e = oracle.PoaSession(1), EmuSession(ring_rows=int(rng.integers(1, 6)))
+        for s in seqs:
+            assert np.array_equal(o.add(s), e.add(s))
+        assert np.array_equal(o.graph()["rank_node"], e.rank_to_node())
+        assert o.consensus() == e.consensus()
+        assert o.msa() == e.msa()
+        o.close()
+        e.close()
+
+
+def test_margin_columns_equals_reference_loop(oracle):
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        n = int(rng.integers(1, 30))
+        row = "".join(rng.choice(list("ACGT-"), n))
+        nog = row.replace("-", "")
+        k5, k3 = int(rng.integers(0, 6)), int(rng.integers(0, 6))
+        f5 = nog[:k5] if rng.random() < 0.7 else "".join(rng.choice(list("ACGT"), k5))
+        f3 = nog[len(nog) - k3:] if (rng.random() < 0.7 and k3 > 0) else "".join(rng.choice(list("ACGT"), k3))
+        assert oracle.call_margin(row, f5, f3).tolist() == batch.margin_columns(row, f5, f3).tolist()
+
+
+def test_encode_rejects_foreign_symbols():
+    assert batch.encode_msa(["ATCG-", "atcg-"]).tolist() == [[0, 1, 2, 3, 4]] * 2
+    with pytest.raises(KeyError):
+        batch.encode_msa(["ACGN"])
+
+
+def test_lpt_shards_cover_and_balance():
+    costs = [float(c) for c in np.random.default_rng(1).integers(1, 100, 57)]
+    for n in (1, 2, 4, 8):
+        sh = shard.lpt_shards(costs, n)
+        assert sorted(i for s in sh for i in s) == list(range(57))
+        loads = [sum(costs[i] for i in s) for s in sh]
+        assert max(loads) - min(loads) <= max(costs)
+    assert shard.lpt_shards(costs, 4) == shard.lpt_shards(costs, 4)
+
+
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    costs = [5.0, 1.0, 3.0, 2.0, 9.0, 4.0, 7.0]
+    mine = shard.my_shard(costs, rank, world)
+    recs = [["chr1", str(i), str(i + 1), rank] for i in mine]
+    full = shard.gather_records(mine, recs, len(costs), group=shard.host_group())
+    if rank == 0:
+        q.put(full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    full = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in full] == [str(i) for i in range(7)]
+    assert {r[3] for r in full} == {0, 1}
+
+
+def test_synth_formats(tmp_path):
+    w = synth.make_small_window(3)
+    assert len(w) == 5 and w[0][0].startswith(w[2]) and w[0][0].endswith(w[3])
+    assert set("".join(w[0])) <= set("ACGT")
+    p = str(tmp_path / "b.npz")
+    synth.save_npz(p, [w, synth.make_small_window(4)])
+    back = synth.load_npz(p)
+    assert back[0][4] == w[4] and list(back[0][1]) == list(w[1]) and back[0][0] == w[0]
+    a, b = synth.make_c2_window(5), synth.make_c2_window(5)
+    assert a[0] == b[0] and a[4] == b[4]
