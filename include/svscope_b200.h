@@ -40,9 +40,13 @@ const char* svs_last_error(const svs_ctx* ctx);
 const char* svs_version(void);
 /* Options (all optional): "poa_threads" CTA size of the alignment kernel (128|256|512),
  * "ring_rows" packed rows kept in shared memory, "workers" host threads that own graphs and
- * streams, "arena_mb" device scratch arena in MiB (0 = 70 % of free memory). */
+ * streams, "arena_mb" device scratch arena in MiB (0 = 85 % of free memory). */
 int svs_set_option(svs_ctx* ctx, const char* key, int64_t value);
 int64_t svs_get_option(const svs_ctx* ctx, const char* key);
+
+/* Measures the issue rate of the integer pipes (G thread-operations/s) for add, max, xor and
+ * fused add+max chains; the denominator of the integer-ALU roofline of the alignment kernel. */
+int svs_int_alu_probe(svs_ctx* ctx, double* gops, int n);
 
 /* ---- read sets ------------------------------------------------------------------------ */
 /* Copies n_seqs sequences (concatenated, 1 byte per base, seq i = seqs[off[i]..off[i+1]))
@@ -72,7 +76,8 @@ int svs_poa_result_copy(const svs_poa_result* res, uint8_t* consensus, uint8_t* 
  * [3] sum of traceback-kernel ms, [4] wall ms of the call, [5] launches of the DP kernel,
  * [6] launches of the traceback kernel, [7] bytes host->device, [8] bytes device->host,
  * [9] algorithmic bytes (read + graph + path), [10] exported rows,
- * [11] graph rows total */
+ * [11] graph rows total, [12..15] host ms summed over workers: waiting for the device,
+ * merging paths into graphs, exporting rank-ordered graphs, packing the staging buffer */
 int svs_poa_result_stats(const svs_poa_result* res, double* stats, int n_stats);
 void svs_poa_result_free(svs_poa_result* res);
 

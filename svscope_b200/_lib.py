@@ -27,6 +27,7 @@ SYMBOLS = {
     "svs_version": (ctypes.c_char_p, []),
     "svs_set_option": (ctypes.c_int, [c_vp, ctypes.c_char_p, ctypes.c_int64]),
     "svs_get_option": (ctypes.c_int64, [c_vp, ctypes.c_char_p]),
+    "svs_int_alu_probe": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int]),
     "svs_reads_upload": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_vp)]),
     "svs_reads_free": (None, [c_vp]),
     "svs_poa_batch": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64] + [ctypes.c_int] * 8 + [ctypes.POINTER(c_vp)]),
@@ -105,6 +106,11 @@ class Context:
 
     def get_option(self, key: str) -> int:
         return int(load().svs_get_option(self._h, key.encode()))
+
+    def int_alu_probe(self):
+        out = np.zeros(4, np.float64)
+        self.check(load().svs_int_alu_probe(self._h, ptr(out), 4))
+        return dict(add=float(out[0]), max=float(out[1]), xor=float(out[2]), addmax=float(out[3]))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -36,6 +36,14 @@ N_STEPS = 20           # ReadsCluster.py:190
 MAX_C = 9              # ReadsCluster.py:221
 
 
+# byte / launch accounting of the auxiliary kernels (filled by the wrappers below)
+ACCT: Dict[str, float] = {}
+
+
+def _acct(key: str, v: float) -> None:
+    ACCT[key] = ACCT.get(key, 0.0) + float(v)
+
+
 def read_tag(read_id: str) -> str:
     return read_id.split("|")[0].split("_")[-1]
 
@@ -106,6 +114,9 @@ def msa_features(ctx: Context, encs: List[np.ndarray], drops: List[np.ndarray], 
     cut = np.ascontiguousarray(cutoffs, np.float64)
     ctx.check(load().svs_msa_features(ctx._h, nw, ptr(enc_cat), ptr(enc_off), ptr(rows), ptr(cols), ptr(drop_cat),
                                       ptr(col_off), ptr(cut), ptr(keep), ptr(nf), ptr(zp), ptr(ident), ptr(id_off)))
+    _acct("feat_h2d_bytes", enc_cat.nbytes + drop_cat.nbytes)
+    _acct("feat_d2h_bytes", keep.nbytes + ident.nbytes + nf.nbytes + zp.nbytes)
+    _acct("aux_launches", 2)
     out = []
     for w in range(nw):
         n = int(rows[w])
@@ -170,6 +181,9 @@ def em_batch(ctx: Context, Xs: List[np.ndarray], tasks: List[EmTaskSpec], want_t
                                   ptr(lab_off), N_STEPS, ptr(steps), 1 if want_theta else 0, ptr(gamma),
                                   ptr(g_off), ptr(theta) if need_theta else None, ptr(t_off), ptr(pi), ptr(p_off),
                                   ptr(lik), ptr(l_off), ptr(status)))
+    _acct("em_h2d_bytes", x_cat.nbytes + lab_cat.nbytes + pi.nbytes + (theta.nbytes if any_theta_in else 0))
+    _acct("em_d2h_bytes", gamma.nbytes + pi.nbytes + lik.nbytes + status.nbytes + (theta.nbytes if want_theta else 0))
+    _acct("aux_launches", len({(int(k), int(n) > 256) for k, n in zip(K, N)}))
     out = []
     for i in range(nt):
         n, k, f = int(N[i]), int(K[i]), int(nf[i])
@@ -196,6 +210,8 @@ def edit_distance_matrices(ctx: Context, reads: ReadSet, groups: Sequence[Sequen
     mem = members if members.size else np.zeros(1, np.int64)
     ctx.check(load().svs_edit_distance_matrix(ctx._h, reads._h, ptr(mem), ptr(goff), ng, ptr(dist), ptr(doff),
                                               ptr(stats), 4))
+    _acct("ed_d2h_bytes", 4.0 * float(stats[3]))
+    _acct("aux_launches", 1)
     mats = [dist[doff[g]:doff[g + 1]].reshape(len(groups[g]), len(groups[g])).copy() for g in range(ng)]
     return mats, dict(cells=float(stats[0]), ms=float(stats[1]), bytes=float(stats[2]), pairs=float(stats[3]))
 
@@ -311,6 +327,7 @@ def localgraph_batch(windows, ctx: Optional[Context] = None, reads: Optional[Rea
     in HBM); otherwise the sequences are uploaded here."""
     ctx = ctx or Context.default()
     tm: Dict[str, float] = {}
+    ACCT.clear()
     t0 = time.perf_counter()
     nw = len(windows)
     flags = list(windowFlags) if windowFlags is not None else ["NormalOutput"] * nw
@@ -440,6 +457,7 @@ def localgraph_batch(windows, ctx: Optional[Context] = None, reads: Optional[Rea
     tm["total"] = time.perf_counter() - t0
     stats = {"poa_" + k: st_msa[k] + st_cons[k] for k in st_msa}
     stats.update({"ed_" + k: v for k, v in st_ed.items()})
+    stats.update(ACCT)
     stats["windows"] = nw
     stats["windows_live"] = len(live)
     stats["windows_em"] = len(em_idx)

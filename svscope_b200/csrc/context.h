@@ -14,11 +14,13 @@ struct svs_ctx {
   int device = 0;
   std::string error;
   // options
-  int poa_threads = 256;
+  int poa_threads = 512;
   int ring_rows = 12;
   int workers = 4;
   int64_t arena_mb = 0;
-  int tb_mode = 0;
+  int lane_jobs = 0;   // alignments per round of a lane (0 = derived)
+  int inflight = 0;    // (unused by the round scheduler)
+  int streams = 0;     // concurrent round streams (0 = 2)
   // device arena shared by the batched calls (allocated lazily, reused)
   void* arena = nullptr;
   size_t arena_bytes = 0;

@@ -16,7 +16,8 @@
 // dependency into two independent max-plus prefix scans.
 //
 // Instead of keeping five score matrices for an equality-test traceback, every cell emits a
-// 16-bit code holding exactly the decisions that traceback would take there:
+// code holding exactly the decisions that traceback would take there (16 bits; rows with a
+// single predecessor keep only the low byte, their in-edge indices being 0):
 //   bits 0-1  move that defines H: 0 diagonal, 1 vertical, 2 horizontal
 //   bit  2    "extend" flag of a vertical / horizontal move (gap continues)
 //   bit  3    horizontal continuation: E[j]+e==E[j+1] || Q[j]+c==Q[j+1]
@@ -165,8 +166,8 @@ SVS_HD uint16_t row0_code(const Scores& s, int32_t j) {
 // Walks the stored decisions from (best_row, L) back to (0, 0) and writes the alignment
 // pairs (node id | -1, read position | -1) in REVERSE order.  Returns the number of pairs,
 // or -1 if `cap` pairs do not suffice.
-SVS_HD int32_t traceback_walk(uint32_t best_row, uint32_t L, const uint16_t* codes, uint64_t ldc,
-                              const uint16_t* col0code, const uint32_t* pred_off,
+SVS_HD int32_t traceback_walk(uint32_t best_row, uint32_t L, const uint8_t* codes, uint32_t w1, uint32_t w2,
+                              const uint32_t* single_before, const uint16_t* col0code, const uint32_t* pred_off,
                               const uint32_t* preds, const uint32_t* node_id, const Scores& s,
                               int32_t* out_pairs, int32_t cap) {
   uint32_t i = best_row, j = L;
@@ -174,7 +175,10 @@ SVS_HD int32_t traceback_walk(uint32_t best_row, uint32_t L, const uint16_t* cod
   auto code_at = [&](uint32_t ii, uint32_t jj) -> uint32_t {
     if (ii == 0) return jj == 0 ? 0u : row0_code(s, static_cast<int32_t>(jj));
     if (jj == 0) return col0code[ii];
-    return codes[static_cast<uint64_t>(ii - 1) * ldc + (jj - 1)];
+    const uint64_t n1 = single_before[ii];
+    const uint8_t* row = codes + n1 * w1 + (static_cast<uint64_t>(ii - 1) - n1) * w2;
+    if (pred_off[ii + 1] - pred_off[ii] == 1) return row[jj - 1];   // 1-byte code: in-edge indices are 0
+    return reinterpret_cast<const uint16_t*>(row)[jj - 1];
   };
   auto pred_row = [&](uint32_t ii, uint32_t k) -> uint32_t {
     return k == kNoPred ? 0u : preds[pred_off[ii] + k];

@@ -244,9 +244,14 @@ void PoaGraph::export_ranked(const PoaScoring& sc, uint32_t ring_rows, RankedGra
     out->col0code[i] = make_code(kMoveVert, ext, 0, stop, kH, kU);
   }
   uint32_t slot = 0;
+  out->single_before.assign(R + 2, 0);
+  uint32_t singles = 0;
   for (uint32_t i = 1; i <= R; ++i) {
     if (out->flags[i] & kFlagExport) out->xslot[i] = static_cast<int32_t>(slot++);
+    out->single_before[i] = singles;
+    if (out->pred_off[i + 1] - out->pred_off[i] == 1) ++singles;
   }
+  out->single_before[R + 1] = singles;
   out->n_export = slot;
 }
 

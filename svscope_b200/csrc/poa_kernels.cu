@@ -49,22 +49,22 @@ struct Stage {
   int32_t psrc[kPredCap];
   int32_t pbh[kPredCap];
   int32_t xslot[kRowBatch];
+  uint32_t single_before[kRowBatch];
   int32_t bA[kRowBatch], bE[kRowBatch], bQ[kRowBatch];
   uint8_t letter[kRowBatch];
   uint8_t flags[kRowBatch];
 };
 
+// The dynamic programme of one alignment, executed by the whole CTA.
 template <int T>
-__global__ void __launch_bounds__(T, 512 / T) poa_dp_kernel(const PoaTask* __restrict__ tasks, const Scores s,
-                                                   const int ring_rows) {
+__device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, const int ring_rows,
+                                         unsigned char* smem_raw) {
   constexpr int NW = T / 32;
   constexpr int WC = T * kC;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t* ring = reinterpret_cast<int32_t*>(smem_raw);
   WarpPub* pub = reinterpret_cast<WarpPub*>(ring + static_cast<size_t>(ring_rows) * WC);
   Stage& st = *reinterpret_cast<Stage*>(pub + 2 * NW);
 
-  const PoaTask tk = tasks[blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t R = tk.R, L = tk.L;
   const uint64_t bstride = static_cast<uint64_t>(R) + 1;
@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(T, 512 / T) poa_dp_kernel(const PoaTask* __res
         st.letter[tid] = tk.letter[i];
         st.flags[tid] = tk.flags[i];
         st.xslot[tid] = tk.xslot[i];
+        st.single_before[tid] = tk.single_before[i];
         if (pass == 0) {
           st.bA[tid] = tk.h0[i];
           st.bE[tid] = kNeg;
@@ -290,8 +291,15 @@ __global__ void __launch_bounds__(T, 512 / T) poa_dp_kernel(const PoaTask* __res
           if (c == c_end) hsel = H;
         }
         if (active) {
-          *reinterpret_cast<uint4*>(tk.codes + static_cast<uint64_t>(i - 1) * tk.ldc + (j0 - 1)) =
-              make_uint4(cw[0], cw[1], cw[2], cw[3]);
+          const uint64_t n1 = st.single_before[r];
+          uint8_t* crow = tk.codes + n1 * tk.w1 + (static_cast<uint64_t>(i - 1) - n1) * tk.w2;
+          if (ne - nb == 1) {  // single predecessor: low bytes only
+            const uint32_t lo = (cw[0] & 0xffu) | ((cw[0] >> 8) & 0xff00u) | ((cw[1] & 0xffu) << 16) | ((cw[1] & 0xff0000u) << 8);
+            const uint32_t hi = (cw[2] & 0xffu) | ((cw[2] >> 8) & 0xff00u) | ((cw[3] & 0xffu) << 16) | ((cw[3] & 0xff0000u) << 8);
+            *reinterpret_cast<uint2*>(crow + (j0 - 1)) = make_uint2(lo, hi);
+          } else {
+            *reinterpret_cast<uint4*>(crow + 2 * static_cast<uint64_t>(j0 - 1)) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+          }
           int32_t* rrow = ring + static_cast<size_t>(slot) * WC + kC * tid;
           *reinterpret_cast<int4*>(rrow) = make_int4(wprev[0], wprev[1], wprev[2], wprev[3]);
           *reinterpret_cast<int4*>(rrow + 4) = make_int4(wprev[4], wprev[5], wprev[6], wprev[7]);
@@ -324,12 +332,54 @@ __global__ void __launch_bounds__(T, 512 / T) poa_dp_kernel(const PoaTask* __res
   }
 }
 
+template <int T>
+__global__ void __launch_bounds__(T, 512 / T) poa_dp_kernel(const PoaTask* __restrict__ tasks, const Scores s,
+                                                            const int ring_rows) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const PoaTask tk = tasks[blockIdx.x];
+  dp_align<T>(tk, s, ring_rows, smem_raw);
+}
+
+// Persistent variant: one CTA per SM pulls alignments (sorted largest first) from a device
+// counter, keeps its traceback codes / exported rows / strip boundaries in the scratch slot
+// of its SM (slot = %smid: with > 114 KB of shared memory only one such CTA fits an SM), and
+// walks the traceback itself as soon as the dynamic programme of the alignment is done.
+template <int T>
+__global__ void __launch_bounds__(T, 512 / T) poa_persistent_kernel(const PoaTask* __restrict__ tasks, const int n_tasks,
+                                                                    int* __restrict__ counter, uint8_t* slot_base,
+                                                                    const uint64_t slot_bytes, const Scores s,
+                                                                    const int ring_rows) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_next;
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  uint8_t* slot = slot_base + static_cast<uint64_t>(smid) * slot_bytes;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_next = atomicAdd(counter, 1);
+    __syncthreads();
+    const int idx = s_next;
+    if (idx >= n_tasks) break;
+    PoaTask tk = tasks[idx];
+    tk.codes = slot + tk.off_codes;
+    tk.xrows = reinterpret_cast<int32_t*>(slot + tk.off_xrows);
+    tk.bnd = reinterpret_cast<int32_t*>(slot + tk.off_bnd);
+    dp_align<T>(tk, s, ring_rows, smem_raw);
+    if (threadIdx.x == 0) {
+      const int32_t n = traceback_walk(static_cast<uint32_t>(tk.result[0]), tk.L, tk.codes, tk.w1, tk.w2,
+                                       tk.single_before, tk.col0code, tk.pred_off, tk.preds, tk.node_id, s,
+                                       tk.path, static_cast<int32_t>(tk.path_cap));
+      tk.result[2] = n;
+    }
+  }
+}
+
 __global__ void poa_tb_kernel(const PoaTask* __restrict__ tasks, const Scores s, const int n_tasks) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_tasks) return;
   const PoaTask tk = tasks[idx];
-  const int32_t n = traceback_walk(static_cast<uint32_t>(tk.result[0]), tk.L, tk.codes, tk.ldc,
-                                   tk.col0code, tk.pred_off, tk.preds, tk.node_id, s, tk.path,
+  const int32_t n = traceback_walk(static_cast<uint32_t>(tk.result[0]), tk.L, tk.codes, tk.w1, tk.w2,
+                                   tk.single_before, tk.col0code, tk.pred_off, tk.preds, tk.node_id, s, tk.path,
                                    static_cast<int32_t>(tk.path_cap));
   tk.result[2] = n;
 }
@@ -363,6 +413,21 @@ cudaError_t poa_dp_launch(const PoaTask* d_tasks, int n_tasks, const Scores& s, 
     case 512: poa_dp_kernel<512><<<n_tasks, 512, smem, stream>>>(d_tasks, s, ring_rows); break;
     default: return cudaErrorInvalidValue;
   }
+  return cudaGetLastError();
+}
+
+cudaError_t poa_persistent_configure(int threads, int ring_rows) {
+  const int bytes = static_cast<int>(poa_dp_smem_bytes(threads, ring_rows));
+  if (threads != 512 || bytes <= 114 * 1024) return cudaErrorInvalidValue;  // must be 1 CTA per SM
+  return cudaFuncSetAttribute(poa_persistent_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+cudaError_t poa_persistent_launch(const PoaTask* d_tasks, int n_tasks, int* d_counter, uint8_t* slot_base,
+                                  uint64_t slot_bytes, int n_sm, const Scores& s, int ring_rows, cudaStream_t stream) {
+  if (n_tasks <= 0) return cudaSuccess;
+  const size_t smem = poa_dp_smem_bytes(512, ring_rows);
+  const int grid = n_tasks < n_sm ? n_tasks : n_sm;
+  poa_persistent_kernel<512><<<grid, 512, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, s, ring_rows);
   return cudaGetLastError();
 }
 

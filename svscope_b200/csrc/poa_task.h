@@ -16,12 +16,16 @@ struct PoaTask {
   const int32_t* h0;          // [R+1] H[row][0]
   const uint16_t* col0code;   // [R+1] traceback codes of column 0
   const uint32_t* node_id;    // [R+1]
+  const uint32_t* single_before;  // [R+2] number of single-predecessor rows among rows 1..i-1
   const uint8_t* read;        // [L]
   uint32_t R, L;
   uint32_t strip, npass;      // columns per pass (multiple of 8), number of passes
   // scratch
-  uint16_t* codes;            // [R][ldc] traceback codes of columns 1..L
-  uint64_t ldc;
+  // traceback codes of columns 1..L: rows with one predecessor store 1 byte per cell (row
+  // pitch w1), rows with several store 2 bytes per cell (row pitch w2); row i starts at byte
+  // single_before[i]*w1 + (i-1-single_before[i])*w2
+  uint8_t* codes;
+  uint32_t w1, w2;
   int32_t* xrows;             // [n_export][ldx] packed cells of exported rows, column j at 3+j
   uint64_t ldx;
   int32_t* bnd;               // [2][4][R+1] strip boundary state (H, A, E, Q), ping-pong
@@ -30,6 +34,8 @@ struct PoaTask {
   int32_t* path;              // [2*path_cap] alignment pairs in reverse order
   uint32_t path_cap;
   uint32_t pad_;
+  // persistent kernel: scratch offsets inside the per-SM slot (codes/xrows/bnd are patched)
+  uint64_t off_codes, off_xrows, off_bnd;
 };
 
 }  // namespace svs

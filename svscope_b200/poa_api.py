@@ -10,7 +10,9 @@ from . import _lib
 from ._lib import Context, ReadSet, c_vp, load, ptr
 
 STAT_NAMES = ["cells", "alignments", "dp_ms", "tb_ms", "wall_ms", "dp_launches", "tb_launches",
-              "h2d_bytes", "d2h_bytes", "algo_bytes", "exported_rows", "rows"]
+              "h2d_bytes", "d2h_bytes", "algo_bytes", "exported_rows", "rows", "host_wait_ms", "host_merge_ms",
+              "host_plan_ms", "host_pack_ms", "refill_ms", "starved_polls", "launch_ms", "final_ms", "inflight_ms",
+              "h2d_ms", "d2h_ms"]
 DEFAULT_SCORES = dict(m=5, n=-4, g=-8, e=-6, q=-10, c=-4)
 
 
@@ -41,8 +43,8 @@ def poa_groups(ctx: Context, reads: ReadSet, groups: Sequence[Sequence[int]], al
         cbuf = np.zeros(max(int(clen[:ng].sum()), 1), np.uint8)
         mbuf = np.zeros(max(int((rows[:ng] * cols[:ng]).sum()), 1), np.uint8)
         load().svs_poa_result_copy(res, ptr(cbuf), ptr(mbuf) if want_msa else None)
-        stats = np.zeros(16, np.float64)
-        load().svs_poa_result_stats(res, ptr(stats), 16)
+        stats = np.zeros(24, np.float64)
+        load().svs_poa_result_stats(res, ptr(stats), 24)
     finally:
         load().svs_poa_result_free(res)
     cons, msas = [], []

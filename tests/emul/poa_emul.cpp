@@ -30,7 +30,10 @@ static void emu_align(Emu* E, const uint8_t* read, uint32_t L) {
   const uint32_t R = G.R;
   const uint64_t W = L + 1;
   std::vector<int32_t> P((R + 1) * W);          // packed cells, all rows
-  std::vector<uint16_t> codes(static_cast<uint64_t>(R) * L);
+  // code rows: 1 byte per cell for single-predecessor rows, 2 bytes otherwise (as on the device)
+  const uint32_t w1 = (L + 7 + 15) / 16 * 16, w2 = (L + 7 + 7) / 8 * 8 * 2;
+  const uint64_t n1_total = G.single_before[R + 1];
+  std::vector<uint8_t> codes(n1_total * w1 + (R - n1_total) * w2 + 64);
   P[0] = pack_cell(0, kNeg, kNeg);
   for (uint32_t j = 1; j <= L; ++j) P[j] = pack_cell(row0_h(s, j), kNeg, kNeg);
   int32_t best = INT32_MIN;
@@ -50,7 +53,11 @@ static void emu_align(Emu* E, const uint8_t* read, uint32_t L) {
         else cell_predk(a, kk, Hp, Fp, Op, unpack_h(P[p * W + j - 1]), sub, s);
       }
       int32_t H;
-      codes[static_cast<uint64_t>(i - 1) * L + (j - 1)] = cell_finish(a, cy, s, H);
+      const uint16_t cd = cell_finish(a, cy, s, H);
+      const uint64_t n1 = G.single_before[i];
+      uint8_t* crow = codes.data() + n1 * w1 + (static_cast<uint64_t>(i - 1) - n1) * w2;
+      if (G.pred_off[i + 1] - G.pred_off[i] == 1) crow[j - 1] = static_cast<uint8_t>(cd);
+      else reinterpret_cast<uint16_t*>(crow)[j - 1] = cd;
       P[i * W + j] = pack_cell(H, a.Fm, a.Om);
     }
     if ((G.flags[i] & kFlagSink) && cy.H > best) {
@@ -59,7 +66,7 @@ static void emu_align(Emu* E, const uint8_t* read, uint32_t L) {
     }
   }
   std::vector<int32_t> rev(2 * (static_cast<uint64_t>(R) + L + 2));
-  const int32_t n = traceback_walk(best_row, L, codes.data(), L, G.col0code.data(), G.pred_off.data(),
+  const int32_t n = traceback_walk(best_row, L, codes.data(), w1, w2, G.single_before.data(), G.col0code.data(), G.pred_off.data(),
                                    G.preds.data(), G.node_id.data(), s, rev.data(),
                                    static_cast<int32_t>(R + L + 2));
   for (int32_t k = n - 1; k >= 0; --k) {
