@@ -276,8 +276,8 @@ class Scheduler {
     tp->R = g.R;
     tp->L = seq_len(tp->seq_id);
     const int64_t worst = 10;  // |penalties| <= 10 checked at entry
-    if (worst * (static_cast<int64_t>(tp->R) + tp->L + 2) >= kMaxScoreSpan) {
-      set_err(SVS_ERR_UNSUPPORTED, "alignment too large for 27-bit scores");
+    if (worst * (static_cast<int64_t>(tp->R) + tp->L + 2) >= kMaxKeySpan) {
+      set_err(SVS_ERR_UNSUPPORTED, "alignment too large for 25-bit scores (|V| + L must stay below 1.6 M)");
       return false;
     }
     const uint32_t cpp = static_cast<uint32_t>(poa_dp_cols_per_pass(ctx_->poa_threads));

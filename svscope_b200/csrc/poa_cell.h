@@ -77,80 +77,130 @@ SVS_HD int32_t row0_h(const Scores& s, int32_t j) {
   return j == 0 ? 0 : imax(row0_e(s, j), row0_q(s, j));
 }
 
-// Running decisions of one cell over its predecessor rows.  `meta` packs the first in-edge
-// index attaining each maximum and the flags taken there:
-//   bits 0-4 kF, 5-9 kO, 10-14 kD, 15-19 kV, bit 20 sF (open H+g attains F), bit 21 sO (open
-//   H+q attains O), bit 22 xV (the vertical move at kV is a gap extension).
+// Running state of one cell over its predecessor rows (four registers).  Single-predecessor
+// rows: Fm, Om, D = the F, O and diagonal candidates, meta = flags.  Rows with several
+// predecessors: the same fields hold max-keys (see cell_pred_key).
 struct CellAcc {
-  int32_t Fm, Om, D;  // maxima of the F, O and diagonal candidates; V = max(Fm, Om)
+  int32_t Fm, Om, D;
   uint32_t meta;
 };
-
-// first predecessor (k = 0)
-SVS_HD void cell_pred0(CellAcc& a, int32_t Hp, int32_t Fp, int32_t Op, int32_t Hpl, int32_t sub,
-                       const Scores& s) {
-  const int32_t G = Hp + s.g, Fe = Fp + s.e, Oq = Hp + s.q, Oe = Op + s.c;
-  a.Fm = imax(G, Fe);
-  a.Om = imax(Oq, Oe);
-  a.D = Hpl + sub;
-  const int32_t V = imax(a.Fm, a.Om);
-  const uint32_t sF = G >= Fe, sO = Oq >= Oe;
-  const uint32_t xV = (Fe == V) || (G != V && Oe == V);
-  a.meta = (sF << 20) | (sO << 21) | (xV << 22);
-}
-
-// further predecessors (k >= 1): strict ">" keeps the first in-edge that attains a maximum
-SVS_HD void cell_predk(CellAcc& a, uint32_t k, int32_t Hp, int32_t Fp, int32_t Op, int32_t Hpl,
-                       int32_t sub, const Scores& s) {
-  const int32_t G = Hp + s.g, Fe = Fp + s.e, Oq = Hp + s.q, Oe = Op + s.c;
-  const int32_t Fc = imax(G, Fe), Oc = imax(Oq, Oe), Dk = Hpl + sub;
-  const int32_t Vk = imax(Fc, Oc);
-  const int32_t Vcur = imax(a.Fm, a.Om);
-  if (Vk > Vcur) {
-    const uint32_t xk = (Fe == Vk) || (G != Vk && Oe == Vk);
-    a.meta = (a.meta & ~((31u << 15) | (1u << 22))) | (k << 15) | (xk << 22);
-  }
-  if (Fc > a.Fm) {
-    a.Fm = Fc;
-    a.meta = (a.meta & ~(31u | (1u << 20))) | k | (static_cast<uint32_t>(G >= Fe) << 20);
-  }
-  if (Oc > a.Om) {
-    a.Om = Oc;
-    a.meta = (a.meta & ~((31u << 5) | (1u << 21))) | (k << 5) | (static_cast<uint32_t>(Oq >= Oe) << 21);
-  }
-  if (Dk > a.D) {
-    a.D = Dk;
-    a.meta = (a.meta & ~(31u << 10)) | (k << 10);
-  }
-}
 
 // State of the previous column of the same row.
 struct RowCarry {
   int32_t A, E, Q, H;
 };
 
-// Completes a cell once the horizontal state of the previous column is known.
-SVS_HD uint16_t cell_finish(const CellAcc& a, RowCarry& cy, const Scores& s, int32_t& H_out) {
-  const int32_t E = imax(cy.A + s.g, cy.E + s.e);
-  const int32_t Q = imax(cy.A + s.q, cy.Q + s.c);
+// ---- fast path for rows with a single predecessor (most rows) --------------------------------
+// With one predecessor every in-edge index is 0 and the vertical candidates depend on the
+// predecessor only through H and the five low bits (dF, dO) of its packed word:
+//   F = H + g + max(0, (e-g) - dF),  O = H + q + max(0, (c-q) - dO),
+// and the two flags taken at the predecessor (xV: a vertical move is an extension, sF: the F
+// maximum is the gap open) are pure functions of (dF, dO): 32-entry truth tables.
+struct SingleTables {
+  uint32_t xv_mask;   // bit (dF*8+dO): vertical move would be a gap extension
+  uint32_t sf_mask;   // bit (dF*8+dO): H+g attains F (stop flag of the extension walk)
+  uint32_t so_mask;   // bit (dF*8+dO): H+q attains O
+};
+
+SVS_HD SingleTables make_single_tables(const Scores& s) {
+  SingleTables t{0u, 0u, 0u};
+  for (int low = 0; low < 32; ++low) {
+    const int32_t dF = (low >> 3) & 3, dO = low & 7;
+    const int32_t G = s.g, Fe = -dF + s.e, Oq = s.q, Oe = -dO + s.c;
+    const int32_t V = imax(imax(G, Fe), imax(Oq, Oe));
+    if ((Fe == V) || (G != V && Oe == V)) t.xv_mask |= 1u << low;
+    if (G >= Fe) t.sf_mask |= 1u << low;
+    if (Oq >= Oe) t.so_mask |= 1u << low;
+  }
+  return t;
+}
+
+// Result: a.Fm, a.Om, a.D as in the general path; a.meta = xV | sF << 1.
+SVS_HD void cell_pred_single(CellAcc& a, int32_t w, int32_t Hpl, int32_t sub, const Scores& s,
+                             const SingleTables& t) {
+  const int32_t Hp = w >> 5;
+  const int32_t dF = (w >> 3) & 3, dO = w & 7;
+  a.Fm = Hp + s.g + imax((s.e - s.g) - dF, 0);
+  a.Om = Hp + s.q + imax((s.c - s.q) - dO, 0);
+  a.D = Hpl + sub;
+  const uint32_t low = static_cast<uint32_t>(w) & 31u;
+  a.meta = ((t.xv_mask >> low) & 1u) | (((t.sf_mask >> low) & 1u) << 1);
+}
+
+// Completes a single-predecessor cell; returns the low byte of the code (indices are 0).
+SVS_HD uint32_t cell_finish_single(const CellAcc& a, RowCarry& cy, const Scores& s, int32_t& H_out) {
+  const int32_t eo = cy.A + s.g, ee = cy.E + s.e, qo = cy.A + s.q, qe = cy.Q + s.c;
+  const int32_t E = imax(eo, ee), Q = imax(qo, qe);
   const int32_t V = imax(a.Fm, a.Om);
   const int32_t A = imax(a.D, V);
   const int32_t H = imax(A, imax(E, Q));
-  const uint32_t kF = a.meta & 31, kO = (a.meta >> 5) & 31;
-  uint32_t move, ext, km;
-  if (a.D == H) {
-    move = kMoveDiag; ext = 0; km = (a.meta >> 10) & 31;
-  } else if (V == H) {
-    move = kMoveVert; ext = (a.meta >> 22) & 1; km = (a.meta >> 15) & 31;
-  } else {
-    move = kMoveHorz; km = 0;
-    ext = (cy.E + s.e == H) || (cy.H + s.g != H && cy.Q + s.c == H);
-  }
+  const bool is_d = (a.D == H), is_v = (V == H);
+  const uint32_t hx = (ee == H) || (cy.H + s.g != H && qe == H);
+  const uint32_t move = is_d ? kMoveDiag : (is_v ? kMoveVert : kMoveHorz);
+  const uint32_t ext = is_d ? 0u : (is_v ? (a.meta & 1u) : hx);
   const uint32_t lcnext = (E + s.e >= A + s.g) || (Q + s.c >= A + s.q);
-  const uint32_t ku = kF <= kO ? kF : kO;
-  const uint32_t stop = kF <= kO ? (a.meta >> 20) & 1 : (a.meta >> 21) & 1;
   cy.A = A; cy.E = E; cy.Q = Q; cy.H = H;
   H_out = H;
+  return move | (ext << 2) | (lcnext << 3) | ((a.meta & 2u) << 3);
+}
+
+// ---- rows with several predecessors: "first in-edge attaining the maximum" by key ---------------
+// A candidate value v of in-edge k with flag f is folded as the single integer
+//   key = v*64 + (31-k)*2 + f ,
+// so that one max() keeps the largest value, among equal values the smallest in-edge index,
+// and carries the flag of that in-edge along (|v| < 2^24 is checked on the host).
+// CellAcc is reused: Fm = key of F, Om = key of O, D = key of the diagonal, meta = key of V.
+constexpr int64_t kMaxKeySpan = 1 << 24;
+
+SVS_HD void cell_pred_key(CellAcc& a, uint32_t k, int32_t w, int32_t Hpl, int32_t sub, const Scores& s,
+                          const SingleTables& t) {
+  const int32_t Hp = w >> 5;
+  const int32_t dF = (w >> 3) & 3, dO = w & 7;
+  const uint32_t low = static_cast<uint32_t>(w) & 31u;
+  const int32_t Fc = Hp + s.g + imax((s.e - s.g) - dF, 0);
+  const int32_t Oc = Hp + s.q + imax((s.c - s.q) - dO, 0);
+  const int32_t Vk = imax(Fc, Oc);
+  const int32_t Dk = Hpl + sub;
+  const int32_t base = static_cast<int32_t>(31u - k) * 2;
+  const int32_t kf = Fc * 64 + base + static_cast<int32_t>((t.sf_mask >> low) & 1u);
+  const int32_t ko = Oc * 64 + base + static_cast<int32_t>((t.so_mask >> low) & 1u);
+  const int32_t kv = Vk * 64 + base + static_cast<int32_t>((t.xv_mask >> low) & 1u);
+  const int32_t kd = Dk * 64 + base;
+  if (k == 0) {
+    a.Fm = kf; a.Om = ko; a.D = kd; a.meta = static_cast<uint32_t>(kv);
+  } else {
+    a.Fm = imax(a.Fm, kf);
+    a.Om = imax(a.Om, ko);
+    a.D = imax(a.D, kd);
+    a.meta = static_cast<uint32_t>(imax(static_cast<int32_t>(a.meta), kv));
+  }
+}
+
+// value of the cell state a successor needs (for packing / the scan)
+SVS_HD int32_t key_value(int32_t key) { return key >> 6; }
+
+SVS_HD uint16_t cell_finish_key(const CellAcc& a, RowCarry& cy, const Scores& s, int32_t& H_out,
+                                int32_t& F_out, int32_t& O_out) {
+  const int32_t kV = static_cast<int32_t>(a.meta);
+  const int32_t Fm = a.Fm >> 6, Om = a.Om >> 6, D = a.D >> 6, V = kV >> 6;
+  const int32_t eo = cy.A + s.g, ee = cy.E + s.e, qo = cy.A + s.q, qe = cy.Q + s.c;
+  const int32_t E = imax(eo, ee), Q = imax(qo, qe);
+  const int32_t A = imax(D, V);
+  const int32_t H = imax(A, imax(E, Q));
+  const bool is_d = (D == H), is_v = (V == H);
+  const uint32_t hx = (ee == H) || (cy.H + s.g != H && qe == H);
+  const uint32_t move = is_d ? kMoveDiag : (is_v ? kMoveVert : kMoveHorz);
+  const uint32_t ext = is_d ? 0u : (is_v ? static_cast<uint32_t>(kV & 1) : hx);
+  const uint32_t km = is_d ? 31u - ((static_cast<uint32_t>(a.D) >> 1) & 31u)
+                           : (is_v ? 31u - ((static_cast<uint32_t>(kV) >> 1) & 31u) : 0u);
+  const uint32_t lcnext = (E + s.e >= A + s.g) || (Q + s.c >= A + s.q);
+  // vertical-extension walk: first in-edge attaining F or O (F wins ties)
+  const uint32_t iF = 31u - ((static_cast<uint32_t>(a.Fm) >> 1) & 31u);
+  const uint32_t iO = 31u - ((static_cast<uint32_t>(a.Om) >> 1) & 31u);
+  const uint32_t ku = iF <= iO ? iF : iO;
+  const uint32_t stop = iF <= iO ? static_cast<uint32_t>(a.Fm & 1) : static_cast<uint32_t>(a.Om & 1);
+  cy.A = A; cy.E = E; cy.Q = Q; cy.H = H;
+  H_out = H; F_out = Fm; O_out = Om;
   return make_code(move, ext, lcnext, stop, km, ku);
 }
 

@@ -57,8 +57,8 @@ struct Stage {
 
 // The dynamic programme of one alignment, executed by the whole CTA.
 template <int T>
-__device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, const int ring_rows,
-                                         unsigned char* smem_raw) {
+__device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, const SingleTables& tabs,
+                                         const int ring_rows, unsigned char* smem_raw) {
   constexpr int NW = T / 32;
   constexpr int WC = T * kC;
   int32_t* ring = reinterpret_cast<int32_t*>(smem_raw);
@@ -140,6 +140,7 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
         const uint32_t i = i0 + r;
         const uint32_t nb = st.poff[r], ne = st.poff[r + 1];
         const int32_t letter = st.letter[r];
+        const bool single = (ne - nb == 1);
         CellAcc acc[kC];
 #pragma unroll
         for (int c = 0; c < kC; ++c) { acc[c].Fm = 0; acc[c].Om = 0; acc[c].D = 0; acc[c].meta = 0; }
@@ -173,22 +174,18 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
               w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
               w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
             }
-            if (e == nb) {
+            if (single) {
 #pragma unroll
               for (int c = 0; c < kC; ++c) {
-                int32_t Hp, Fp, Op;
-                unpack_cell(w[c], Hp, Fp, Op);
-                cell_pred0(acc[c], Hp, Fp, Op, hl, (letter == rd[c]) ? s.m : s.n, s);
-                hl = Hp;
+                cell_pred_single(acc[c], w[c], hl, (letter == rd[c]) ? s.m : s.n, s, tabs);
+                hl = unpack_h(w[c]);
               }
             } else {
               const uint32_t k = e - nb;
 #pragma unroll
               for (int c = 0; c < kC; ++c) {
-                int32_t Hp, Fp, Op;
-                unpack_cell(w[c], Hp, Fp, Op);
-                cell_predk(acc[c], k, Hp, Fp, Op, hl, (letter == rd[c]) ? s.m : s.n, s);
-                hl = Hp;
+                cell_pred_key(acc[c], k, w[c], hl, (letter == rd[c]) ? s.m : s.n, s, tabs);
+                hl = unpack_h(w[c]);
               }
             }
           }
@@ -199,7 +196,8 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
         int32_t el = kNeg, ql = kNeg, eloc7 = kNeg, qloc7 = kNeg;
 #pragma unroll
         for (int c = 0; c < kC; ++c) {
-          const int32_t A = imax(acc[c].D, imax(acc[c].Fm, acc[c].Om));
+          const int32_t A = single ? imax(acc[c].D, imax(acc[c].Fm, acc[c].Om))
+                                   : imax(key_value(acc[c].D), key_value(static_cast<int32_t>(acc[c].meta)));
           if (c == kC - 1) { eloc7 = el; qloc7 = ql; a7 = A; }
           el = imax(A + s.g, el + s.e);
           ql = imax(A + s.q, ql + s.c);
@@ -282,18 +280,29 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
         // ---- phase 2: H, traceback codes, packed row --------------------------------------
         uint32_t cw[kC / 2];
         int32_t hsel = INT32_MIN;
+        if (single) {
 #pragma unroll
-        for (int c = 0; c < kC; ++c) {
-          int32_t H;
-          const uint32_t cd = cell_finish(acc[c], cy, s, H);
-          wprev[c] = pack_cell(H, acc[c].Fm, acc[c].Om);
-          if (c & 1) cw[c >> 1] |= cd << 16; else cw[c >> 1] = cd;
-          if (c == c_end) hsel = H;
+          for (int c = 0; c < kC; ++c) {
+            int32_t H;
+            const uint32_t cd = cell_finish_single(acc[c], cy, s, H);
+            wprev[c] = pack_cell(H, acc[c].Fm, acc[c].Om);
+            if (c & 1) cw[c >> 1] |= cd << 16; else cw[c >> 1] = cd;
+            if (c == c_end) hsel = H;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < kC; ++c) {
+            int32_t H, Fv, Ov;
+            const uint32_t cd = cell_finish_key(acc[c], cy, s, H, Fv, Ov);
+            wprev[c] = pack_cell(H, Fv, Ov);
+            if (c & 1) cw[c >> 1] |= cd << 16; else cw[c >> 1] = cd;
+            if (c == c_end) hsel = H;
+          }
         }
         if (active) {
           const uint64_t n1 = st.single_before[r];
           uint8_t* crow = tk.codes + n1 * tk.w1 + (static_cast<uint64_t>(i - 1) - n1) * tk.w2;
-          if (ne - nb == 1) {  // single predecessor: low bytes only
+          if (single) {  // single predecessor: low bytes only
             const uint32_t lo = (cw[0] & 0xffu) | ((cw[0] >> 8) & 0xff00u) | ((cw[1] & 0xffu) << 16) | ((cw[1] & 0xff0000u) << 8);
             const uint32_t hi = (cw[2] & 0xffu) | ((cw[2] >> 8) & 0xff00u) | ((cw[3] & 0xffu) << 16) | ((cw[3] & 0xff0000u) << 8);
             *reinterpret_cast<uint2*>(crow + (j0 - 1)) = make_uint2(lo, hi);
@@ -334,10 +343,10 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
 
 template <int T>
 __global__ void __launch_bounds__(T, 512 / T) poa_dp_kernel(const PoaTask* __restrict__ tasks, const Scores s,
-                                                            const int ring_rows) {
+                                                            const SingleTables tabs, const int ring_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PoaTask tk = tasks[blockIdx.x];
-  dp_align<T>(tk, s, ring_rows, smem_raw);
+  dp_align<T>(tk, s, tabs, ring_rows, smem_raw);
 }
 
 // Persistent variant: one CTA per SM pulls alignments (sorted largest first) from a device
@@ -348,7 +357,7 @@ template <int T>
 __global__ void __launch_bounds__(T, 512 / T) poa_persistent_kernel(const PoaTask* __restrict__ tasks, const int n_tasks,
                                                                     int* __restrict__ counter, uint8_t* slot_base,
                                                                     const uint64_t slot_bytes, const Scores s,
-                                                                    const int ring_rows) {
+                                                                    const SingleTables tabs, const int ring_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_next;
   unsigned smid;
@@ -364,7 +373,7 @@ __global__ void __launch_bounds__(T, 512 / T) poa_persistent_kernel(const PoaTas
     tk.codes = slot + tk.off_codes;
     tk.xrows = reinterpret_cast<int32_t*>(slot + tk.off_xrows);
     tk.bnd = reinterpret_cast<int32_t*>(slot + tk.off_bnd);
-    dp_align<T>(tk, s, ring_rows, smem_raw);
+    dp_align<T>(tk, s, tabs, ring_rows, smem_raw);
     if (threadIdx.x == 0) {
       const int32_t n = traceback_walk(static_cast<uint32_t>(tk.result[0]), tk.L, tk.codes, tk.w1, tk.w2,
                                        tk.single_before, tk.col0code, tk.pred_off, tk.preds, tk.node_id, s,
@@ -408,9 +417,9 @@ cudaError_t poa_dp_launch(const PoaTask* d_tasks, int n_tasks, const Scores& s, 
   if (n_tasks <= 0) return cudaSuccess;
   const size_t smem = poa_dp_smem_bytes(threads, ring_rows);
   switch (threads) {
-    case 128: poa_dp_kernel<128><<<n_tasks, 128, smem, stream>>>(d_tasks, s, ring_rows); break;
-    case 256: poa_dp_kernel<256><<<n_tasks, 256, smem, stream>>>(d_tasks, s, ring_rows); break;
-    case 512: poa_dp_kernel<512><<<n_tasks, 512, smem, stream>>>(d_tasks, s, ring_rows); break;
+    case 128: poa_dp_kernel<128><<<n_tasks, 128, smem, stream>>>(d_tasks, s, make_single_tables(s), ring_rows); break;
+    case 256: poa_dp_kernel<256><<<n_tasks, 256, smem, stream>>>(d_tasks, s, make_single_tables(s), ring_rows); break;
+    case 512: poa_dp_kernel<512><<<n_tasks, 512, smem, stream>>>(d_tasks, s, make_single_tables(s), ring_rows); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -427,7 +436,8 @@ cudaError_t poa_persistent_launch(const PoaTask* d_tasks, int n_tasks, int* d_co
   if (n_tasks <= 0) return cudaSuccess;
   const size_t smem = poa_dp_smem_bytes(512, ring_rows);
   const int grid = n_tasks < n_sm ? n_tasks : n_sm;
-  poa_persistent_kernel<512><<<grid, 512, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, s, ring_rows);
+  poa_persistent_kernel<512><<<grid, 512, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, s,
+                                                         make_single_tables(s), ring_rows);
   return cudaGetLastError();
 }
 

@@ -36,6 +36,7 @@ static void emu_align(Emu* E, const uint8_t* read, uint32_t L) {
   std::vector<uint8_t> codes(n1_total * w1 + (R - n1_total) * w2 + 64);
   P[0] = pack_cell(0, kNeg, kNeg);
   for (uint32_t j = 1; j <= L; ++j) P[j] = pack_cell(row0_h(s, j), kNeg, kNeg);
+  const SingleTables tabs = make_single_tables(s);
   int32_t best = INT32_MIN;
   uint32_t best_row = 0;
   for (uint32_t i = 1; i <= R; ++i) {
@@ -44,19 +45,25 @@ static void emu_align(Emu* E, const uint8_t* read, uint32_t L) {
     for (uint32_t j = 1; j <= L; ++j) {
       CellAcc a;
       const int32_t sub = (G.letter[i] == read[j - 1]) ? s.m : s.n;
-      for (uint32_t k = G.pred_off[i]; k < G.pred_off[i + 1]; ++k) {
-        const uint32_t p = G.preds[k];
-        int32_t Hp, Fp, Op;
-        unpack_cell(P[p * W + j], Hp, Fp, Op);
-        const uint32_t kk = k - G.pred_off[i];
-        if (kk == 0) cell_pred0(a, Hp, Fp, Op, unpack_h(P[p * W + j - 1]), sub, s);
-        else cell_predk(a, kk, Hp, Fp, Op, unpack_h(P[p * W + j - 1]), sub, s);
-      }
+      const bool single = (G.pred_off[i + 1] - G.pred_off[i] == 1);
       int32_t H;
-      const uint16_t cd = cell_finish(a, cy, s, H);
+      uint16_t cd;
+      if (single) {  // the kernels' fast path
+        const uint32_t p = G.preds[G.pred_off[i]];
+        cell_pred_single(a, P[p * W + j], unpack_h(P[p * W + j - 1]), sub, s, tabs);
+        cd = static_cast<uint16_t>(cell_finish_single(a, cy, s, H));
+      } else {
+        for (uint32_t k = G.pred_off[i]; k < G.pred_off[i + 1]; ++k) {
+          const uint32_t p = G.preds[k];
+          cell_pred_key(a, k - G.pred_off[i], P[p * W + j], unpack_h(P[p * W + j - 1]), sub, s, tabs);
+        }
+        int32_t Fo, Oo;
+        cd = cell_finish_key(a, cy, s, H, Fo, Oo);
+        a.Fm = Fo; a.Om = Oo;
+      }
       const uint64_t n1 = G.single_before[i];
       uint8_t* crow = codes.data() + n1 * w1 + (static_cast<uint64_t>(i - 1) - n1) * w2;
-      if (G.pred_off[i + 1] - G.pred_off[i] == 1) crow[j - 1] = static_cast<uint8_t>(cd);
+      if (single) crow[j - 1] = static_cast<uint8_t>(cd);
       else reinterpret_cast<uint16_t*>(crow)[j - 1] = cd;
       P[i * W + j] = pack_cell(H, a.Fm, a.Om);
     }
