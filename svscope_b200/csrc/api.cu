@@ -1,4 +1,5 @@
 // Context, options and read-set entry points of the C ABI (include/svscope_b200.h).
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -11,6 +12,12 @@ namespace {
 // Integer-ALU issue-rate probe: 8 independent dependent chains per thread so that the pipe,
 // not the 4-cycle latency, limits.  kind 0: add (IADD3), 1: max (VIMNMX), 2: xor (LOP3),
 // 3: fused add+max as the DP uses it.
+__global__ void nsmid_kernel(unsigned* out) {
+  unsigned n;
+  asm volatile("mov.u32 %0, %%nsmid;" : "=r"(n));
+  out[0] = n;
+}
+
 template <int KIND>
 __global__ void alu_probe_kernel(int32_t* out, int iters, int32_t seed) {
   int32_t a[8];
@@ -69,6 +76,17 @@ int svs_create(int device, svs_ctx** out) {
   ctx->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  // %smid indexes the per-SM scratch slots of the persistent alignment kernel: size them by
+  // %nsmid (upper bound of %smid), which may exceed the number of enabled SMs
+  ctx->n_smid = ctx->sm_count;
+  unsigned* d_n = nullptr;
+  if (cudaMalloc(&d_n, sizeof(unsigned)) == cudaSuccess) {
+    unsigned h_n = 0;
+    nsmid_kernel<<<1, 1>>>(d_n);
+    if (cudaMemcpy(&h_n, d_n, sizeof(unsigned), cudaMemcpyDeviceToHost) == cudaSuccess && h_n > 0)
+      ctx->n_smid = std::max<int>(ctx->sm_count, static_cast<int>(h_n));
+    cudaFree(d_n);
+  }
   *out = ctx;
   return SVS_OK;
 }
@@ -129,6 +147,7 @@ int64_t svs_get_option(const svs_ctx* ctx, const char* key) {
   if (k == "streams") return ctx->streams;
   if (k == "arena_mb") return ctx->arena_bytes ? static_cast<int64_t>(ctx->arena_bytes >> 20) : ctx->arena_mb;
   if (k == "sm_count") return ctx->sm_count;
+  if (k == "n_smid") return ctx->n_smid;
   return -1;
 }
 

@@ -25,6 +25,7 @@ struct svs_ctx {
   void* arena = nullptr;
   size_t arena_bytes = 0;
   int sm_count = 0;
+  int n_smid = 0;      // upper bound of %smid
   std::mutex mu;
 };
 

@@ -13,6 +13,7 @@
 // Integer/logic work only, bound by the ALU pipes; reads stream once from HBM.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -37,19 +38,21 @@ __device__ __forceinline__ int sym_of(uint8_t ch) { return (ch >> 1) & 3; }  // 
 // owns the last pattern row of the strip) the sum of horizontal deltas at that row.
 template <int W>
 __device__ int strip_pass(const PairTask& t, int row0, int rows, bool first_strip, bool last_strip, int lane) {
-  uint32_t peq[W][4], pv[W], mv[W];
+  // pattern as two bit planes of the 2-bit symbol (half the registers of four match masks);
+  // rows past the end of the pattern hold arbitrary bits: carries only travel upwards, so they
+  // never reach the score row
+  uint32_t b0[W], b1[W], pv[W], mv[W];
 #pragma unroll
   for (int w = 0; w < W; ++w) {
     pv[w] = 0xffffffffu; mv[w] = 0;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) peq[w][s] = 0;
+    b0[w] = 0; b1[w] = 0;
     const int base = (lane * W + w) * 32;
     for (int bit = 0; bit < 32; ++bit) {
       const int r = base + bit;
       if (r < rows) {
-        const int s = sym_of(t.a[row0 + r]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) peq[w][q] |= (s == q) ? (1u << bit) : 0u;
+        const uint32_t s = static_cast<uint32_t>(sym_of(t.a[row0 + r]));
+        b0[w] |= (s & 1u) << bit;
+        b1[w] |= (s >> 1) << bit;
       }
     }
   }
@@ -73,12 +76,10 @@ __device__ int strip_pass(const PairTask& t, int row0, int rows, bool first_stri
     }
     int hout = hin;
     if (valid) {
+      const uint32_t m0 = 0u - static_cast<uint32_t>(sym & 1), m1 = 0u - static_cast<uint32_t>(sym >> 1);
 #pragma unroll
       for (int w = 0; w < W; ++w) {
-        uint32_t eq = peq[w][0];
-        eq = (sym == 1) ? peq[w][1] : eq;
-        eq = (sym == 2) ? peq[w][2] : eq;
-        eq = (sym == 3) ? peq[w][3] : eq;
+        uint32_t eq = ~((b0[w] ^ m0) | (b1[w] ^ m1));
         const uint32_t Pv = pv[w], Mv = mv[w];
         const uint32_t xv = eq | Mv;
         if (hout < 0) eq |= 1u;
@@ -118,27 +119,50 @@ __device__ int pair_distance(const PairTask& t, int lane) {
   return total;
 }
 
-__global__ void __launch_bounds__(128) myers_kernel(const PairTask* __restrict__ tasks, int32_t* __restrict__ dist,
-                                                    int n_pairs) {
+// One kernel per words-per-lane class, so that short patterns are not compiled with (and do not
+// pay the occupancy of) the register footprint of the longest ones.
+template <int W>
+__global__ void __launch_bounds__(128, (W <= 16 ? 4 : (W <= 24 ? 3 : 2))) myers_kernel(const PairTask* __restrict__ tasks, const int32_t* __restrict__ ids,
+                                                    int32_t* __restrict__ dist, int n_pairs) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n_pairs) return;
-  const PairTask t = tasks[warp];
+  const int id = ids[warp];
+  const PairTask t = tasks[id];
   int d;
   if (t.la == 0) d = t.lb;
   else if (t.lb == 0) d = t.la;
-  else {
-    const int words = (t.la + 1023) / 1024;  // words per lane needed for a single strip
-    if (words <= 1) d = pair_distance<1>(t, lane);
-    else if (words <= 2) d = pair_distance<2>(t, lane);
-    else if (words <= 4) d = pair_distance<4>(t, lane);
-    else if (words <= 8) d = pair_distance<8>(t, lane);
-    else if (words <= 12) d = pair_distance<12>(t, lane);
-    else if (words <= 16) d = pair_distance<16>(t, lane);
-    else if (words <= 24) d = pair_distance<24>(t, lane);
-    else d = pair_distance<kMaxW>(t, lane);
+  else d = pair_distance<W>(t, lane);
+  if (lane == 0) dist[id] = d;
+}
+
+constexpr int kClasses[] = {1, 2, 4, 6, 8, 10, 12, 16, 24, 32};
+constexpr int kNumClasses = 10;
+
+int class_of(int32_t la) {
+  const int words = (la + 1023) / 1024;
+  for (int c = 0; c < kNumClasses; ++c)
+    if (words <= kClasses[c]) return c;
+  return kNumClasses - 1;  // longer patterns run strip by strip with 32 words per lane
+}
+
+cudaError_t launch_class(int c, const PairTask* d_tasks, const int32_t* d_ids, int32_t* d_dist, int n) {
+  if (n <= 0) return cudaSuccess;
+  const int block = 128;
+  const unsigned blocks = static_cast<unsigned>((static_cast<int64_t>(n) * 32 + block - 1) / block);
+  switch (kClasses[c]) {
+    case 1: myers_kernel<1><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
+    case 2: myers_kernel<2><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
+    case 4: myers_kernel<4><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
+    case 6: myers_kernel<6><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
+    case 8: myers_kernel<8><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
+    case 10: myers_kernel<10><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
+    case 12: myers_kernel<12><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
+    case 16: myers_kernel<16><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
+    case 24: myers_kernel<24><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
+    default: myers_kernel<32><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
   }
-  if (lane == 0) dist[warp] = d;
+  return cudaGetLastError();
 }
 
 int run_pairs(svs_ctx* ctx, const svs_reads* reads, const std::vector<int64_t>& a, const std::vector<int64_t>& b,
@@ -164,10 +188,10 @@ int run_pairs(svs_ctx* ctx, const svs_reads* reads, const std::vector<int64_t>& 
     cells += static_cast<double>(la) * static_cast<double>(lb);
     bytes += static_cast<double>(la + lb) + 4;
   }
-  PairTask* d_tasks = nullptr; int32_t* d_dist = nullptr; int8_t* d_bnd = nullptr;
+  PairTask* d_tasks = nullptr; int32_t* d_dist = nullptr; int8_t* d_bnd = nullptr; int32_t* d_ids = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   auto cleanup = [&]() {
-    cudaFree(d_tasks); cudaFree(d_dist); cudaFree(d_bnd);
+    cudaFree(d_tasks); cudaFree(d_dist); cudaFree(d_bnd); cudaFree(d_ids);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
   };
@@ -188,11 +212,28 @@ int run_pairs(svs_ctx* ctx, const svs_reads* reads, const std::vector<int64_t>& 
   SVS_CU(cudaMemcpy(d_tasks, tasks.data(), n * sizeof(PairTask), cudaMemcpyHostToDevice));
   SVS_CU(cudaEventCreate(&e0));
   SVS_CU(cudaEventCreate(&e1));
-  const int block = 128;
-  const int64_t blocks = (n * 32 + block - 1) / block;
+  // pairs grouped by words-per-lane class; inside a class longest text first
+  std::vector<std::vector<int32_t>> by_class(kNumClasses);
+  for (int64_t k = 0; k < n; ++k) by_class[class_of(tasks[k].la)].push_back(static_cast<int32_t>(k));
+  std::vector<int32_t> ids;
+  std::vector<size_t> coff(kNumClasses + 1, 0);
+  for (int c = 0; c < kNumClasses; ++c) {
+    auto& v = by_class[c];
+    std::sort(v.begin(), v.end(), [&](int32_t x, int32_t y) { return tasks[x].lb > tasks[y].lb; });
+    coff[c] = ids.size();
+    ids.insert(ids.end(), v.begin(), v.end());
+  }
+  coff[kNumClasses] = ids.size();
+  SVS_CU(cudaMalloc(&d_ids, n * sizeof(int32_t)));
+  SVS_CU(cudaMemcpy(d_ids, ids.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
   SVS_CU(cudaEventRecord(e0));
-  myers_kernel<<<static_cast<unsigned>(blocks), block>>>(d_tasks, d_dist, static_cast<int>(n));
-  SVS_CU(cudaGetLastError());
+  int launches = 0;
+  for (int c = kNumClasses - 1; c >= 0; --c) {
+    const int nc = static_cast<int>(by_class[c].size());
+    if (!nc) continue;
+    SVS_CU(launch_class(c, d_tasks, d_ids + coff[c], d_dist, nc));
+    ++launches;
+  }
   SVS_CU(cudaEventRecord(e1));
   SVS_CU(cudaDeviceSynchronize());
   float ms = 0;
@@ -201,8 +242,8 @@ int run_pairs(svs_ctx* ctx, const svs_reads* reads, const std::vector<int64_t>& 
 #undef SVS_CU
   cleanup();
   if (stats) {
-    const double v[4] = {cells, static_cast<double>(ms), bytes, static_cast<double>(n)};
-    for (int k = 0; k < n_stats && k < 4; ++k) stats[k] = v[k];
+    const double v[5] = {cells, static_cast<double>(ms), bytes, static_cast<double>(n), static_cast<double>(launches)};
+    for (int k = 0; k < n_stats && k < 5; ++k) stats[k] = v[k];
   }
   return SVS_OK;
 }

@@ -176,10 +176,11 @@ class Scheduler {
     // persistent mode needs exactly one resident CTA per SM (512 threads, > 114 KB shared memory);
     // otherwise every alignment takes the classic path with explicit arena blocks
     persistent_ = ctx_->poa_threads == 512 && poa_dp_smem_bytes(512, ctx_->ring_rows) > 114 * 1024;
-    slot_bytes_ = persistent_ ? (static_cast<size_t>(static_cast<double>(ctx_->arena_bytes) * 0.88) / n_sm_) / 4096 * 4096 : 0;
+    n_slots_ = std::max(n_sm_, ctx_->n_smid);
+    slot_bytes_ = persistent_ ? (static_cast<size_t>(static_cast<double>(ctx_->arena_bytes) * 0.88) / n_slots_) / 4096 * 4096 : 0;
     slot_base_ = static_cast<uint8_t*>(ctx_->arena);
-    block_base_ = slot_base_ + slot_bytes_ * n_sm_;
-    block_bytes_ = ctx_->arena_bytes - slot_bytes_ * n_sm_;
+    block_base_ = slot_base_ + slot_bytes_ * n_slots_;
+    block_bytes_ = ctx_->arena_bytes - slot_bytes_ * n_slots_;
     blocks_.reset(block_bytes_);
     const int ns = std::max(1, std::min(ctx_->streams > 0 ? ctx_->streams : 2, njobs));
     streams_.resize(ns);
@@ -545,7 +546,7 @@ class Scheduler {
   Scores s_;
   svs_poa_result* res_;
   bool want_msa_;
-  int threads_ = 1, n_sm_ = 1;
+  int threads_ = 1, n_sm_ = 1, n_slots_ = 1;
   bool persistent_ = false;
   size_t slot_bytes_ = 0, block_bytes_ = 0;
   uint8_t* slot_base_ = nullptr;

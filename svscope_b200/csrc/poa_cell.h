@@ -41,6 +41,7 @@ constexpr uint32_t kNoPred = 31;
 constexpr uint32_t kMaxIndeg = 31;        // in-edge index must fit 5 bits, 31 is reserved
 constexpr int64_t kMaxScoreSpan = 1 << 26;
 constexpr uint8_t kFlagSink = 1, kFlagExport = 4;  // per-row flags of the ranked graph
+constexpr uint8_t kFlagChain = 8;  // the row has exactly one predecessor and it is the previous row
 
 struct Scores {
   int32_t m, n, g, e, q, c;
@@ -213,60 +214,81 @@ SVS_HD uint16_t row0_code(const Scores& s, int32_t j) {
   return make_code(kMoveHorz, ext, lcnext, 0, 0, 0);
 }
 
+// Everything the traceback needs to read.
+struct TbView {
+  const uint8_t* codes;
+  uint32_t w1, w2;
+  const uint32_t* single_before;
+  const uint16_t* col0code;
+  const uint32_t* pred_off;
+  const uint32_t* preds;
+  const uint32_t* node_id;
+};
+
+SVS_HD uint32_t tb_code_at(const TbView& v, const Scores& s, uint32_t ii, uint32_t jj) {
+  if (ii == 0) return jj == 0 ? 0u : row0_code(s, static_cast<int32_t>(jj));
+  if (jj == 0) return v.col0code[ii];
+  const uint64_t n1 = v.single_before[ii];
+  const uint8_t* row = v.codes + n1 * v.w1 + (static_cast<uint64_t>(ii - 1) - n1) * v.w2;
+  if (v.pred_off[ii + 1] - v.pred_off[ii] == 1) return row[jj - 1];   // 1-byte code: in-edge indices are 0
+  return reinterpret_cast<const uint16_t*>(row)[jj - 1];
+}
+
+// One iteration of the traceback loop at (i, j) != (0, 0), including the gap-extension walks
+// it may trigger.  Appends pairs (node id | -1, read position | -1) in REVERSE order.
+// Returns false if `cap` pairs do not suffice.
+SVS_HD bool tb_step(const TbView& v, const Scores& s, uint32_t& i, uint32_t& j, int32_t& n, int32_t* out_pairs,
+                    int32_t cap) {
+  auto pred_row = [&](uint32_t ii, uint32_t k) -> uint32_t {
+    return k == kNoPred ? 0u : v.preds[v.pred_off[ii] + k];
+  };
+  const uint32_t cd = tb_code_at(v, s, i, j);
+  const uint32_t move = cd & 3, ext = (cd >> 2) & 1, km = (cd >> 5) & 31;
+  uint32_t pi, pj;
+  if (move == kMoveDiag) { pi = pred_row(i, km); pj = j - 1; }
+  else if (move == kMoveVert) { pi = pred_row(i, km); pj = j; }
+  else { pi = i; pj = j - 1; }
+  if (n >= cap) return false;
+  out_pairs[2 * n] = (i == pi) ? -1 : static_cast<int32_t>(v.node_id[i]);
+  out_pairs[2 * n + 1] = (j == pj) ? -1 : static_cast<int32_t>(j - 1);
+  ++n;
+  i = pi; j = pj;
+  if (move == kMoveHorz && ext) {
+    while (true) {
+      if (n >= cap) return false;
+      out_pairs[2 * n] = -1;
+      out_pairs[2 * n + 1] = static_cast<int32_t>(j - 1);
+      ++n;
+      --j;
+      if (j == 0 || !((tb_code_at(v, s, i, j) >> 3) & 1)) break;
+    }
+  } else if (move == kMoveVert && ext) {
+    while (i != 0) {
+      const uint32_t c2 = tb_code_at(v, s, i, j);
+      const uint32_t stop = (c2 >> 4) & 1, ku = (c2 >> 10) & 31;
+      const uint32_t up = pred_row(i, ku);
+      if (n >= cap) return false;
+      out_pairs[2 * n] = static_cast<int32_t>(v.node_id[i]);
+      out_pairs[2 * n + 1] = -1;
+      ++n;
+      i = up;
+      if (stop || i == 0) break;
+    }
+  }
+  return true;
+}
+
 // Walks the stored decisions from (best_row, L) back to (0, 0) and writes the alignment
-// pairs (node id | -1, read position | -1) in REVERSE order.  Returns the number of pairs,
-// or -1 if `cap` pairs do not suffice.
+// pairs in REVERSE order.  Returns the number of pairs, or -1 if `cap` pairs do not suffice.
 SVS_HD int32_t traceback_walk(uint32_t best_row, uint32_t L, const uint8_t* codes, uint32_t w1, uint32_t w2,
                               const uint32_t* single_before, const uint16_t* col0code, const uint32_t* pred_off,
                               const uint32_t* preds, const uint32_t* node_id, const Scores& s,
                               int32_t* out_pairs, int32_t cap) {
+  const TbView v{codes, w1, w2, single_before, col0code, pred_off, preds, node_id};
   uint32_t i = best_row, j = L;
   int32_t n = 0;
-  auto code_at = [&](uint32_t ii, uint32_t jj) -> uint32_t {
-    if (ii == 0) return jj == 0 ? 0u : row0_code(s, static_cast<int32_t>(jj));
-    if (jj == 0) return col0code[ii];
-    const uint64_t n1 = single_before[ii];
-    const uint8_t* row = codes + n1 * w1 + (static_cast<uint64_t>(ii - 1) - n1) * w2;
-    if (pred_off[ii + 1] - pred_off[ii] == 1) return row[jj - 1];   // 1-byte code: in-edge indices are 0
-    return reinterpret_cast<const uint16_t*>(row)[jj - 1];
-  };
-  auto pred_row = [&](uint32_t ii, uint32_t k) -> uint32_t {
-    return k == kNoPred ? 0u : preds[pred_off[ii] + k];
-  };
   while (!(i == 0 && j == 0)) {
-    const uint32_t cd = code_at(i, j);
-    const uint32_t move = cd & 3, ext = (cd >> 2) & 1, km = (cd >> 5) & 31;
-    uint32_t pi, pj;
-    if (move == kMoveDiag) { pi = pred_row(i, km); pj = j - 1; }
-    else if (move == kMoveVert) { pi = pred_row(i, km); pj = j; }
-    else { pi = i; pj = j - 1; }
-    if (n >= cap) return -1;
-    out_pairs[2 * n] = (i == pi) ? -1 : static_cast<int32_t>(node_id[i]);
-    out_pairs[2 * n + 1] = (j == pj) ? -1 : static_cast<int32_t>(j - 1);
-    ++n;
-    i = pi; j = pj;
-    if (move == kMoveHorz && ext) {
-      while (true) {
-        if (n >= cap) return -1;
-        out_pairs[2 * n] = -1;
-        out_pairs[2 * n + 1] = static_cast<int32_t>(j - 1);
-        ++n;
-        --j;
-        if (j == 0 || !((code_at(i, j) >> 3) & 1)) break;
-      }
-    } else if (move == kMoveVert && ext) {
-      while (i != 0) {
-        const uint32_t c2 = code_at(i, j);
-        const uint32_t stop = (c2 >> 4) & 1, ku = (c2 >> 10) & 31;
-        const uint32_t up = pred_row(i, ku);
-        if (n >= cap) return -1;
-        out_pairs[2 * n] = static_cast<int32_t>(node_id[i]);
-        out_pairs[2 * n + 1] = -1;
-        ++n;
-        i = up;
-        if (stop || i == 0) break;
-      }
-    }
+    if (!tb_step(v, s, i, j, n, out_pairs, cap)) return -1;
   }
   return n;
 }

@@ -249,7 +249,10 @@ void PoaGraph::export_ranked(const PoaScoring& sc, uint32_t ring_rows, RankedGra
   for (uint32_t i = 1; i <= R; ++i) {
     if (out->flags[i] & kFlagExport) out->xslot[i] = static_cast<int32_t>(slot++);
     out->single_before[i] = singles;
-    if (out->pred_off[i + 1] - out->pred_off[i] == 1) ++singles;
+    if (out->pred_off[i + 1] - out->pred_off[i] == 1) {
+      ++singles;
+      if (out->preds[out->pred_off[i]] + 1 == i) out->flags[i] |= kFlagChain;
+    }
   }
   out->single_before[R + 1] = singles;
   out->n_export = slot;

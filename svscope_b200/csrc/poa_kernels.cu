@@ -349,6 +349,54 @@ __global__ void __launch_bounds__(T, 512 / T) poa_dp_kernel(const PoaTask* __res
   dp_align<T>(tk, s, tabs, ring_rows, smem_raw);
 }
 
+// Traceback by one warp.  Long diagonal runs through chain rows (one predecessor = the
+// previous row) are the common case: the 32 lanes look at the cells (i-k, j-k) in parallel
+// and the walk advances by the number of leading lanes whose cell is such a diagonal move;
+// everything else is one serial step of the reference walk (tb_step) by lane 0.
+__device__ void tb_walk_warp(const PoaTask& tk, const Scores& s) {
+  const TbView v{tk.codes, tk.w1, tk.w2, tk.single_before, tk.col0code, tk.pred_off, tk.preds, tk.node_id};
+  const int lane = threadIdx.x & 31;
+  uint32_t i = static_cast<uint32_t>(tk.result[0]), j = tk.L;
+  int32_t n = 0;
+  const int32_t cap = static_cast<int32_t>(tk.path_cap);
+  bool ok = true;
+  while (ok && !(i == 0 && j == 0)) {
+    bool mine = false;
+    int32_t node = 0;
+    if (i > static_cast<uint32_t>(lane) && j > static_cast<uint32_t>(lane)) {
+      const uint32_t r = i - lane, c = j - lane;
+      if (tk.flags[r] & kFlagChain) {
+        const uint64_t n1 = tk.single_before[r];
+        const uint32_t cd = tk.codes[n1 * tk.w1 + (static_cast<uint64_t>(r - 1) - n1) * tk.w2 + (c - 1)];
+        if ((cd & 3u) == kMoveDiag) {
+          mine = true;
+          node = static_cast<int32_t>(tk.node_id[r]);
+        }
+      }
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, mine);
+    const int m = __ffs(~hit) - 1;   // leading lanes with a chain diagonal (32 when all)
+    const int run = m < 0 ? 32 : m;
+    if (run > 0) {
+      if (n + run > cap) { ok = false; break; }
+      if (lane < run) {
+        tk.path[2 * (n + lane)] = node;
+        tk.path[2 * (n + lane) + 1] = static_cast<int32_t>(j - lane - 1);
+      }
+      n += run;
+      i -= run;
+      j -= run;
+    } else {
+      if (lane == 0) ok = tb_step(v, s, i, j, n, tk.path, cap);
+      i = __shfl_sync(0xffffffffu, i, 0);
+      j = __shfl_sync(0xffffffffu, j, 0);
+      n = __shfl_sync(0xffffffffu, n, 0);
+      ok = __shfl_sync(0xffffffffu, static_cast<int>(ok), 0) != 0;
+    }
+  }
+  if (lane == 0) tk.result[2] = ok ? n : -1;
+}
+
 // Persistent variant: one CTA per SM pulls alignments (sorted largest first) from a device
 // counter, keeps its traceback codes / exported rows / strip boundaries in the scratch slot
 // of its SM (slot = %smid: with > 114 KB of shared memory only one such CTA fits an SM), and
@@ -374,12 +422,7 @@ __global__ void __launch_bounds__(T, 512 / T) poa_persistent_kernel(const PoaTas
     tk.xrows = reinterpret_cast<int32_t*>(slot + tk.off_xrows);
     tk.bnd = reinterpret_cast<int32_t*>(slot + tk.off_bnd);
     dp_align<T>(tk, s, tabs, ring_rows, smem_raw);
-    if (threadIdx.x == 0) {
-      const int32_t n = traceback_walk(static_cast<uint32_t>(tk.result[0]), tk.L, tk.codes, tk.w1, tk.w2,
-                                       tk.single_before, tk.col0code, tk.pred_off, tk.preds, tk.node_id, s,
-                                       tk.path, static_cast<int32_t>(tk.path_cap));
-      tk.result[2] = n;
-    }
+    if (threadIdx.x < 32) tb_walk_warp(tk, s);
   }
 }
 
