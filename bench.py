@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before any CUDA context (see svscope_b200/__init__.py)
 
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 55.49e9   # profiles/r01_poa_persistent_kernel_ncu_full.txt
 METRIC = "localGraph windows/sec"
 UNIT = "windows/s"
 WORKLOAD = "configs[1]: synthetic INS/DEL windows, 30 tumor + 30 normal reads, 5-15 kb, 5% error"
@@ -238,8 +239,30 @@ def main():
     def step():
         return localgraph_batch(windows, ctx=ctx, reads=reads, edit_distance=ed)
 
-    for _ in range(args.warmup):
-        out = step()
+    def e2e_step():
+        """Same step through the public batch call with host buffers: the reads are uploaded from
+        page-locked host memory and every result is copied back inside the timed region."""
+        barrier_sync()
+        t0 = time.perf_counter()
+        o2 = localgraph_batch(windows, ctx=ctx, reads=None, edit_distance=ed)
+        torch.cuda.synchronize()
+        barrier_sync()
+        t_e2e = max_over_ranks(time.perf_counter() - t0)
+        s2 = o2.stats
+        h2d = read_bytes + s2["poa_h2d_bytes"] + s2.get("feat_h2d_bytes", 0) + s2.get("em_h2d_bytes", 0)
+        d2h = s2["poa_d2h_bytes"] + s2.get("feat_d2h_bytes", 0) + s2.get("em_d2h_bytes", 0) + s2.get("ed_d2h_bytes", 0)
+        return o2, {"value": sum_over_ranks(float(args.windows)) / t_e2e, "unit": UNIT,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "note": "timed on the last warm-up step" if args.warmup > 0 else "timed after the timed steps"}
+
+    # warm-up steps; the last one doubles as the end-to-end measurement (it is itself preceded by
+    # warm-up steps), which keeps the default run within minutes
+    e2e, o2 = None, None
+    for w in range(args.warmup):
+        if w == args.warmup - 1 and not args.no_e2e:
+            o2, e2e = e2e_step()
+        else:
+            out = step()
     sampler = ClockSampler(local)
     barrier_sync()
     if rank == 0:
@@ -262,22 +285,10 @@ def main():
     t_max = max_over_ranks(max(dev_s, 1e-9))
     total_windows = sum_over_ranks(float(args.windows * args.steps))
     value = total_windows / t_max
-
-    # ---- end to end through the public batch call with host buffers -------------------------
-    e2e = None
-    if not args.no_e2e:
-        barrier_sync()
-        t0 = time.perf_counter()
-        o2 = localgraph_batch(windows, ctx=ctx, reads=None, edit_distance=ed)   # uploads inside
-        torch.cuda.synchronize()
-        barrier_sync()
-        t_e2e = max_over_ranks(time.perf_counter() - t0)
-        assert o2.records == out.records
-        s2 = o2.stats
-        h2d = read_bytes + s2["poa_h2d_bytes"] + s2.get("feat_h2d_bytes", 0) + s2.get("em_h2d_bytes", 0)
-        d2h = s2["poa_d2h_bytes"] + s2.get("feat_d2h_bytes", 0) + s2.get("em_d2h_bytes", 0) + s2.get("ed_d2h_bytes", 0)
-        e2e = {"value": sum_over_ranks(float(args.windows)) / t_e2e, "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+    if e2e is None and not args.no_e2e:
+        o2, e2e = e2e_step()
+    if o2 is not None:
+        assert o2.records == out.records      # resident and host-buffer paths give the same records
 
     if rank != 0:
         return
@@ -296,7 +307,10 @@ def main():
     avg_launch_s = dp_s / n_launch
     achieved_gbs = algo_bytes_per_launch / avg_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved_gbs / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (148 alignments, read 46 of the "
+                                "window-MSA stage) from profiles/r01_poa_persistent_kernel_ncu_full.txt; almost all of it is "
+                                "traceback codes (1-2 B per DP cell), which are implementation traffic, not algorithmic bytes",
                 "kernel": "poa_dp_kernel", "launches_per_step": n_launch,
                 "avg_launch_ms": avg_launch_s * 1e3,
                 "note": "algorithmic bytes = read + rank-ordered graph + alignment path (SURVEY 8d); the kernel is "
@@ -327,7 +341,9 @@ def main():
         "stage_seconds_last_step": {k: round(v, 3) for k, v in out.timings.items()},
         "wall_s_timed": wall, "gen_s": t_gen,
         "poa": {"cells_per_step": st["poa_cells"], "alignments_per_step": st["poa_alignments"],
-                "exported_row_frac": st["poa_exported_rows"] / max(1.0, st["poa_rows"])},
+                "exported_row_frac": st["poa_exported_rows"] / max(1.0, st["poa_rows"]),
+                "host_ms_per_step": {k: st.get("poa_" + k, 0.0) for k in
+                                     ("host_wait_ms", "host_merge_ms", "host_plan_ms", "host_pack_ms", "launch_ms")}},
         "edit_distance": {"cells_per_step": st["ed_cells"], "kernel_ms_per_step": st["ed_ms"],
                           "gcups": st["ed_cells"] / max(st["ed_ms"], 1e-9) / 1e6},
         "em_output_windows": sum(r[-1].endswith("EMOutput") for r in out.records),

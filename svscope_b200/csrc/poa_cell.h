@@ -9,11 +9,19 @@
 //   D[i][j] = max_k H[p_k][j-1] + s                    A[i][j] = max(D, F, O)
 //   E[i][j] = max(A[i][j-1]+g, E[i][j-1]+e)            Q[i][j] = max(A[i][j-1]+q, Q[i][j-1]+c)
 //   H[i][j] = max(A, E, Q)
-// E is opened from A instead of H.  H and Q are unchanged by that and every equality test
-// of the traceback has the same outcome (DESIGN.md "Row scan"): a gap of one piece opened
-// directly on top of a gap of the other piece never defines H, and in the one traceback test
-// where the E values themselves differ the Q alternative decides.  This turns the horizontal
-// dependency into two independent max-plus prefix scans.
+// E is opened from A instead of H (spoa: E[j] = max(H[j-1]+g, E[j-1]+e)).  Why this is exact, for
+// every convex parameter set (q < g < e < c, the only mode supported):
+//  * Q: a Q gap opened on an E-derived H is dominated by the single Q gap from the same origin
+//    (g+(d-1)e+q+(m-1)c < q+(d+m-1)c since g<c, e<c), one opened on a Q-derived H by extending
+//    it (q<c); so Q computed from A equals spoa's Q.
+//  * E: spoa's E can exceed the A-opened E only through "Q run of length d, then E opened on
+//    it"; then the Q run simply continued scores higher by m(c-e)+(e-g) > 0 at every later
+//    column, so H = max(A, E, Q) is the same, and in the traceback tests that involve E
+//    (H == E[j-1]+e;  E[j]+e == E[j+1] || Q[j]+c == Q[j+1]) either the E term is false in both
+//    versions or the Q term is true in both.
+//  * E opened on an E-derived H is dominated by extending (g<e).
+// This turns the horizontal dependency into two independent max-plus prefix scans.
+// tests/test_host_logic.py runs this arithmetic against the five-matrix oracle.
 //
 // Instead of keeping five score matrices for an equality-test traceback, every cell emits a
 // code holding exactly the decisions that traceback would take there (16 bits; rows with a
