@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--workers", type=int, default=0)
     ap.add_argument("--poa-threads", type=int, default=0)
     ap.add_argument("--ring-rows", type=int, default=0)
+    ap.add_argument("--poa-cols", type=int, default=0)
+    ap.add_argument("--streams", type=int, default=0)
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -228,6 +230,10 @@ def main():
         ctx.set_option("poa_threads", args.poa_threads)
     if args.ring_rows:
         ctx.set_option("ring_rows", args.ring_rows)
+    if args.poa_cols:
+        ctx.set_option("poa_cols", args.poa_cols)
+    if args.streams:
+        ctx.set_option("streams", args.streams)
     ed = not args.no_edit_distance
 
     t_gen = time.perf_counter()
@@ -332,7 +338,8 @@ def main():
         "config": {"workload": WORKLOAD, "windows_per_gpu": args.windows, "reads_per_window": 60,
                    "edit_distance_matrix": ed, "l2": "inputs larger than L2 (reads + traceback codes >> 126 MB per step)",
                    "parallelism": f"windows sharded over {world} GPU(s), no collective", "host_workers": workers,
-                   "poa_threads": ctx.get_option("poa_threads"), "ring_rows": ctx.get_option("ring_rows")},
+                   "poa_threads": ctx.get_option("poa_threads"), "poa_cols": ctx.get_option("poa_cols"),
+                   "ring_rows": ctx.get_option("ring_rows")},
         "e2e": e2e,
         "gpu_launches": int(agg.get("poa_dp_launches", 0) + agg.get("poa_tb_launches", 0) + agg.get("aux_launches", 0)),
         "clocks": clocks,

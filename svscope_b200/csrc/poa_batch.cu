@@ -175,7 +175,8 @@ class Scheduler {
     n_sm_ = std::max(1, ctx_->sm_count);
     // persistent mode needs exactly one resident CTA per SM (512 threads, > 114 KB shared memory);
     // otherwise every alignment takes the classic path with explicit arena blocks
-    persistent_ = ctx_->poa_threads == 512 && poa_dp_smem_bytes(512, ctx_->ring_rows) > 114 * 1024;
+    persistent_ = poa_persistent_supported(ctx_->poa_threads, ctx_->ring_rows, ctx_->poa_cols);
+    cols_ = static_cast<uint32_t>(poa_cols_per_thread(ctx_->poa_threads, ctx_->poa_cols));
     n_slots_ = std::max(n_sm_, ctx_->n_smid);
     slot_bytes_ = persistent_ ? (static_cast<size_t>(static_cast<double>(ctx_->arena_bytes) * 0.88) / n_slots_) / 4096 * 4096 : 0;
     slot_base_ = static_cast<uint8_t*>(ctx_->arena);
@@ -281,12 +282,13 @@ class Scheduler {
       set_err(SVS_ERR_UNSUPPORTED, "alignment too large for 25-bit scores (|V| + L must stay below 1.6 M)");
       return false;
     }
-    const uint32_t cpp = static_cast<uint32_t>(poa_dp_cols_per_pass(ctx_->poa_threads));
+    const uint32_t cpp = static_cast<uint32_t>(poa_dp_cols_per_pass(ctx_->poa_threads, ctx_->poa_cols));
+    const uint32_t C = cols_;   // columns per thread: every thread stores C codes / words at once
     tp->npass = (tp->L + cpp - 1) / cpp;
-    tp->strip = ((tp->L + tp->npass - 1) / tp->npass + 7) / 8 * 8;
-    tp->w1 = static_cast<uint32_t>((static_cast<uint64_t>(tp->L) + 7 + 15) / 16 * 16);       // 1 B per cell
-    tp->w2 = static_cast<uint32_t>((static_cast<uint64_t>(tp->L) + 7 + 7) / 8 * 8 * 2);       // 2 B per cell
-    tp->ldx = (static_cast<uint64_t>(tp->L) + 11 + 7) / 8 * 8;
+    tp->strip = ((tp->L + tp->npass - 1) / tp->npass + C - 1) / C * C;
+    tp->w1 = static_cast<uint32_t>((static_cast<uint64_t>(tp->L) + C - 1 + 15) / 16 * 16);       // 1 B per cell
+    tp->w2 = static_cast<uint32_t>((static_cast<uint64_t>(tp->L) + C - 1 + 7) / 8 * 8 * 2);       // 2 B per cell
+    tp->ldx = (static_cast<uint64_t>(tp->L) + 3 + C + 7) / 8 * 8;
     tp->path_cap = tp->R + tp->L + 2;
     const size_t R1 = static_cast<size_t>(g.R) + 1;
     tp->in_bytes = align_up(R1, 16) * 2 /*letter, flags*/ + align_up((R1 + 1) * 4, 16) * 2 /*pred_off, single_before*/ +
@@ -473,9 +475,9 @@ class Scheduler {
               check(cudaEventRecord(st.ev[0], cs), "event");
     if (ok && st.n_slot > 0)
       ok = check(poa_persistent_launch(d_tasks, st.n_slot, st.d_counter, slot_base_, slot_bytes_, n_sm_, s_,
-                                       ctx_->ring_rows, cs), "poa_persistent_kernel");
+                                       ctx_->poa_threads, ctx_->ring_rows, ctx_->poa_cols, cs), "poa_persistent_kernel");
     if (ok && st.n_big > 0)
-      ok = check(poa_dp_launch(d_tasks + st.n_slot, st.n_big, s_, ctx_->poa_threads, ctx_->ring_rows, cs), "poa_dp_kernel");
+      ok = check(poa_dp_launch(d_tasks + st.n_slot, st.n_big, s_, ctx_->poa_threads, ctx_->ring_rows, ctx_->poa_cols, cs), "poa_dp_kernel");
     ok = ok && check(cudaEventRecord(st.ev[1], cs), "event");
     if (ok && st.n_big > 0) ok = check(poa_tb_launch(d_tasks + st.n_slot, st.n_big, s_, cs), "poa_tb_kernel");
     ok = ok && check(cudaEventRecord(st.ev[2], cs), "event") &&
@@ -547,6 +549,7 @@ class Scheduler {
   svs_poa_result* res_;
   bool want_msa_;
   int threads_ = 1, n_sm_ = 1, n_slots_ = 1;
+  uint32_t cols_ = 8;
   bool persistent_ = false;
   size_t slot_bytes_ = 0, block_bytes_ = 0;
   uint8_t* slot_base_ = nullptr;
@@ -574,9 +577,9 @@ int run_jobs(svs_ctx* ctx, const svs_reads* reads, std::vector<PoaJob>& jobs, co
              WorkerStats* total, svs_poa_result* res, bool want_msa) {
   int rc = ensure_arena(ctx);
   if (rc) return rc;
-  SVS_CUDA(ctx, poa_dp_configure(ctx->poa_threads, ctx->ring_rows));
-  if (ctx->poa_threads == 512 && poa_dp_smem_bytes(512, ctx->ring_rows) > 114 * 1024)
-    SVS_CUDA(ctx, poa_persistent_configure(512, ctx->ring_rows));
+  SVS_CUDA(ctx, poa_dp_configure(ctx->poa_threads, ctx->ring_rows, ctx->poa_cols));
+  if (poa_persistent_supported(ctx->poa_threads, ctx->ring_rows, ctx->poa_cols))
+    SVS_CUDA(ctx, poa_persistent_configure(ctx->poa_threads, ctx->ring_rows, ctx->poa_cols));
   Scheduler sched(ctx, reads, s, res, want_msa);
   rc = sched.run(jobs);
   if (rc || sched.err) return fail(ctx, sched.err ? sched.err : rc, sched.errmsg);

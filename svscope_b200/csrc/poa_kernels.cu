@@ -33,7 +33,6 @@ namespace svs {
 
 namespace {
 
-constexpr int kC = 8;            // columns per thread
 constexpr int kRowBatch = 32;    // rows whose metadata is staged in shared memory at once
 constexpr int kPredCap = kRowBatch * 32;
 constexpr int32_t kSrcRow0 = -1;
@@ -56,9 +55,10 @@ struct Stage {
 };
 
 // The dynamic programme of one alignment, executed by the whole CTA.
-template <int T>
+template <int T, int kC>
 __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, const SingleTables& tabs,
                                          const int ring_rows, unsigned char* smem_raw) {
+  static_assert(kC == 8 || kC == 16, "columns per thread");
   constexpr int NW = T / 32;
   constexpr int WC = T * kC;
   int32_t* ring = reinterpret_cast<int32_t*>(smem_raw);
@@ -161,18 +161,20 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
               hl = row0_h(s, static_cast<int32_t>(j0) - 1);
             } else if (src & kSrcGlobal) {
               const int32_t* row = tk.xrows + static_cast<uint64_t>(src & ~kSrcGlobal) * tk.ldx + 3;
-              const int4 v0 = __ldcg(reinterpret_cast<const int4*>(row + j0));
-              const int4 v1 = __ldcg(reinterpret_cast<const int4*>(row + j0 + 4));
+#pragma unroll
+              for (int q = 0; q < kC / 4; ++q) {
+                const int4 v = __ldcg(reinterpret_cast<const int4*>(row + j0 + 4 * q));
+                w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+              }
               hl = unpack_h(__ldcg(row + j0 - 1));
-              w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
-              w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
             } else {
               const int32_t* row = ring + static_cast<size_t>(src) * WC;
-              const int4 v0 = *reinterpret_cast<const int4*>(row + kC * tid);
-              const int4 v1 = *reinterpret_cast<const int4*>(row + kC * tid + 4);
+#pragma unroll
+              for (int q = 0; q < kC / 4; ++q) {
+                const int4 v = *reinterpret_cast<const int4*>(row + kC * tid + 4 * q);
+                w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+              }
               hl = (tid == 0) ? st.pbh[e] : unpack_h(row[kC * tid - 1]);
-              w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
-              w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
             }
             if (single) {
 #pragma unroll
@@ -303,19 +305,28 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
           const uint64_t n1 = st.single_before[r];
           uint8_t* crow = tk.codes + n1 * tk.w1 + (static_cast<uint64_t>(i - 1) - n1) * tk.w2;
           if (single) {  // single predecessor: low bytes only
-            const uint32_t lo = (cw[0] & 0xffu) | ((cw[0] >> 8) & 0xff00u) | ((cw[1] & 0xffu) << 16) | ((cw[1] & 0xff0000u) << 8);
-            const uint32_t hi = (cw[2] & 0xffu) | ((cw[2] >> 8) & 0xff00u) | ((cw[3] & 0xffu) << 16) | ((cw[3] & 0xff0000u) << 8);
-            *reinterpret_cast<uint2*>(crow + (j0 - 1)) = make_uint2(lo, hi);
+            uint32_t b[kC / 4];
+#pragma unroll
+            for (int q = 0; q < kC / 4; ++q)
+              b[q] = (cw[2 * q] & 0xffu) | ((cw[2 * q] >> 8) & 0xff00u) | ((cw[2 * q + 1] & 0xffu) << 16) |
+                     ((cw[2 * q + 1] & 0xff0000u) << 8);
+            if (kC == 8) *reinterpret_cast<uint2*>(crow + (j0 - 1)) = make_uint2(b[0], b[1]);
+            else *reinterpret_cast<uint4*>(crow + (j0 - 1)) = make_uint4(b[0], b[1], b[kC / 4 - 2], b[kC / 4 - 1]);
           } else {
-            *reinterpret_cast<uint4*>(crow + 2 * static_cast<uint64_t>(j0 - 1)) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+#pragma unroll
+            for (int q = 0; q < kC / 8; ++q)
+              *reinterpret_cast<uint4*>(crow + 2 * static_cast<uint64_t>(j0 - 1) + 16 * q) =
+                  make_uint4(cw[4 * q], cw[4 * q + 1], cw[4 * q + 2], cw[4 * q + 3]);
           }
           int32_t* rrow = ring + static_cast<size_t>(slot) * WC + kC * tid;
-          *reinterpret_cast<int4*>(rrow) = make_int4(wprev[0], wprev[1], wprev[2], wprev[3]);
-          *reinterpret_cast<int4*>(rrow + 4) = make_int4(wprev[4], wprev[5], wprev[6], wprev[7]);
+#pragma unroll
+          for (int q = 0; q < kC / 4; ++q)
+            *reinterpret_cast<int4*>(rrow + 4 * q) = make_int4(wprev[4 * q], wprev[4 * q + 1], wprev[4 * q + 2], wprev[4 * q + 3]);
           if (st.flags[r] & kFlagExport) {
             int32_t* xrow = tk.xrows + static_cast<uint64_t>(st.xslot[r]) * tk.ldx + 3;
-            *reinterpret_cast<int4*>(xrow + j0) = make_int4(wprev[0], wprev[1], wprev[2], wprev[3]);
-            *reinterpret_cast<int4*>(xrow + j0 + 4) = make_int4(wprev[4], wprev[5], wprev[6], wprev[7]);
+#pragma unroll
+            for (int q = 0; q < kC / 4; ++q)
+              *reinterpret_cast<int4*>(xrow + j0 + 4 * q) = make_int4(wprev[4 * q], wprev[4 * q + 1], wprev[4 * q + 2], wprev[4 * q + 3]);
             if (tid == 0 && pass == 0) xrow[0] = pack_cell(bA, kNeg, kNeg);
           }
           if (writes_bnd) {
@@ -341,12 +352,12 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
   }
 }
 
-template <int T>
-__global__ void __launch_bounds__(T, 512 / T) poa_dp_kernel(const PoaTask* __restrict__ tasks, const Scores s,
+template <int T, int kC>
+__global__ void __launch_bounds__(T, (kC == 16 ? 1 : 512 / T)) poa_dp_kernel(const PoaTask* __restrict__ tasks, const Scores s,
                                                             const SingleTables tabs, const int ring_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PoaTask tk = tasks[blockIdx.x];
-  dp_align<T>(tk, s, tabs, ring_rows, smem_raw);
+  dp_align<T, kC>(tk, s, tabs, ring_rows, smem_raw);
 }
 
 // Traceback by one warp.  Long diagonal runs through chain rows (one predecessor = the
@@ -401,8 +412,8 @@ __device__ void tb_walk_warp(const PoaTask& tk, const Scores& s) {
 // counter, keeps its traceback codes / exported rows / strip boundaries in the scratch slot
 // of its SM (slot = %smid: with > 114 KB of shared memory only one such CTA fits an SM), and
 // walks the traceback itself as soon as the dynamic programme of the alignment is done.
-template <int T>
-__global__ void __launch_bounds__(T, 512 / T) poa_persistent_kernel(const PoaTask* __restrict__ tasks, const int n_tasks,
+template <int T, int kC>
+__global__ void __launch_bounds__(T, 1) poa_persistent_kernel(const PoaTask* __restrict__ tasks, const int n_tasks,
                                                                     int* __restrict__ counter, uint8_t* slot_base,
                                                                     const uint64_t slot_bytes, const Scores s,
                                                                     const SingleTables tabs, const int ring_rows) {
@@ -421,7 +432,7 @@ __global__ void __launch_bounds__(T, 512 / T) poa_persistent_kernel(const PoaTas
     tk.codes = slot + tk.off_codes;
     tk.xrows = reinterpret_cast<int32_t*>(slot + tk.off_xrows);
     tk.bnd = reinterpret_cast<int32_t*>(slot + tk.off_bnd);
-    dp_align<T>(tk, s, tabs, ring_rows, smem_raw);
+    dp_align<T, kC>(tk, s, tabs, ring_rows, smem_raw);
     if (threadIdx.x < 32) tb_walk_warp(tk, s);
   }
 }
@@ -438,49 +449,70 @@ __global__ void poa_tb_kernel(const PoaTask* __restrict__ tasks, const Scores s,
 
 }  // namespace
 
-size_t poa_dp_smem_bytes(int threads, int ring_rows) {
-  return static_cast<size_t>(ring_rows) * threads * kC * sizeof(int32_t) +
+int poa_cols_per_thread(int threads, int cols) { return (cols == 16 && threads == 256) ? 16 : 8; }
+
+size_t poa_dp_smem_bytes(int threads, int ring_rows, int cols) {
+  return static_cast<size_t>(ring_rows) * threads * poa_cols_per_thread(threads, cols) * sizeof(int32_t) +
          2 * (threads / 32) * sizeof(WarpPub) + sizeof(Stage);
 }
 
-int poa_dp_cols_per_pass(int threads) { return threads * kC; }
+int poa_dp_cols_per_pass(int threads, int cols) { return threads * poa_cols_per_thread(threads, cols); }
 
-cudaError_t poa_dp_configure(int threads, int ring_rows) {
-  const int bytes = static_cast<int>(poa_dp_smem_bytes(threads, ring_rows));
+cudaError_t poa_dp_configure(int threads, int ring_rows, int cols) {
+  const int bytes = static_cast<int>(poa_dp_smem_bytes(threads, ring_rows, cols));
+  if (poa_cols_per_thread(threads, cols) == 16)
+    return cudaFuncSetAttribute(poa_dp_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   switch (threads) {
-    case 128: return cudaFuncSetAttribute(poa_dp_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    case 256: return cudaFuncSetAttribute(poa_dp_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    case 512: return cudaFuncSetAttribute(poa_dp_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    case 128: return cudaFuncSetAttribute(poa_dp_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    case 256: return cudaFuncSetAttribute(poa_dp_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    case 512: return cudaFuncSetAttribute(poa_dp_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     default: return cudaErrorInvalidValue;
   }
 }
 
-cudaError_t poa_dp_launch(const PoaTask* d_tasks, int n_tasks, const Scores& s, int threads,
-                          int ring_rows, cudaStream_t stream) {
+cudaError_t poa_dp_launch(const PoaTask* d_tasks, int n_tasks, const Scores& s, int threads, int ring_rows, int cols,
+                          cudaStream_t stream) {
   if (n_tasks <= 0) return cudaSuccess;
-  const size_t smem = poa_dp_smem_bytes(threads, ring_rows);
+  const size_t smem = poa_dp_smem_bytes(threads, ring_rows, cols);
+  const SingleTables tabs = make_single_tables(s);
+  if (poa_cols_per_thread(threads, cols) == 16) {
+    poa_dp_kernel<256, 16><<<n_tasks, 256, smem, stream>>>(d_tasks, s, tabs, ring_rows);
+    return cudaGetLastError();
+  }
   switch (threads) {
-    case 128: poa_dp_kernel<128><<<n_tasks, 128, smem, stream>>>(d_tasks, s, make_single_tables(s), ring_rows); break;
-    case 256: poa_dp_kernel<256><<<n_tasks, 256, smem, stream>>>(d_tasks, s, make_single_tables(s), ring_rows); break;
-    case 512: poa_dp_kernel<512><<<n_tasks, 512, smem, stream>>>(d_tasks, s, make_single_tables(s), ring_rows); break;
+    case 128: poa_dp_kernel<128, 8><<<n_tasks, 128, smem, stream>>>(d_tasks, s, tabs, ring_rows); break;
+    case 256: poa_dp_kernel<256, 8><<<n_tasks, 256, smem, stream>>>(d_tasks, s, tabs, ring_rows); break;
+    case 512: poa_dp_kernel<512, 8><<<n_tasks, 512, smem, stream>>>(d_tasks, s, tabs, ring_rows); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 
-cudaError_t poa_persistent_configure(int threads, int ring_rows) {
-  const int bytes = static_cast<int>(poa_dp_smem_bytes(threads, ring_rows));
-  if (threads != 512 || bytes <= 114 * 1024) return cudaErrorInvalidValue;  // must be 1 CTA per SM
-  return cudaFuncSetAttribute(poa_persistent_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+// persistent mode needs exactly one resident CTA per SM: > 114 KB of shared memory
+bool poa_persistent_supported(int threads, int ring_rows, int cols) {
+  const bool shape = (threads == 512 && poa_cols_per_thread(threads, cols) == 8) ||
+                     (threads == 256 && poa_cols_per_thread(threads, cols) == 16);
+  return shape && poa_dp_smem_bytes(threads, ring_rows, cols) > 114 * 1024;
+}
+
+cudaError_t poa_persistent_configure(int threads, int ring_rows, int cols) {
+  if (!poa_persistent_supported(threads, ring_rows, cols)) return cudaErrorInvalidValue;
+  const int bytes = static_cast<int>(poa_dp_smem_bytes(threads, ring_rows, cols));
+  if (threads == 512) return cudaFuncSetAttribute(poa_persistent_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return cudaFuncSetAttribute(poa_persistent_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 cudaError_t poa_persistent_launch(const PoaTask* d_tasks, int n_tasks, int* d_counter, uint8_t* slot_base,
-                                  uint64_t slot_bytes, int n_sm, const Scores& s, int ring_rows, cudaStream_t stream) {
+                                  uint64_t slot_bytes, int n_sm, const Scores& s, int threads, int ring_rows, int cols,
+                                  cudaStream_t stream) {
   if (n_tasks <= 0) return cudaSuccess;
-  const size_t smem = poa_dp_smem_bytes(512, ring_rows);
+  const size_t smem = poa_dp_smem_bytes(threads, ring_rows, cols);
   const int grid = n_tasks < n_sm ? n_tasks : n_sm;
-  poa_persistent_kernel<512><<<grid, 512, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, s,
-                                                         make_single_tables(s), ring_rows);
+  const SingleTables tabs = make_single_tables(s);
+  if (threads == 512)
+    poa_persistent_kernel<512, 8><<<grid, 512, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, s, tabs, ring_rows);
+  else
+    poa_persistent_kernel<256, 16><<<grid, 256, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, s, tabs, ring_rows);
   return cudaGetLastError();
 }
 

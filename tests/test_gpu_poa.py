@@ -41,16 +41,18 @@ def _random_group(rng, it, lmax=400):
     return seqs
 
 
-@pytest.mark.parametrize("threads,ring", [(512, 12), (256, 12), (128, 1), (512, 3), (128, 24)])
-def test_alignment_pairs_bit_exact(ctx, oracle, threads, ring):
+@pytest.mark.parametrize("threads,ring,cols", [(512, 12, 8), (256, 12, 16), (256, 12, 8), (128, 1, 8), (512, 3, 8),
+                                               (128, 24, 8), (256, 2, 16)])
+def test_alignment_pairs_bit_exact(ctx, oracle, threads, ring, cols):
     """Every alignment (node id, read position) list equals the oracle's, for several CTA
     sizes and ring depths (ring 1 forces almost every non-adjacent predecessor through the
-    exported rows in global memory).  (512, 12) is the production configuration: persistent
-    kernel, per-SM scratch slots, fused traceback; the others take the classic launch path."""
+    exported rows in global memory).  (512, 12, 8) and (256, 12, 16) are the persistent
+    configurations (per-SM scratch slots, fused traceback); the others take the classic launch path."""
     from svscope_b200.poa_api import align_pairs
     ctx.set_option("poa_threads", threads)
     ctx.set_option("ring_rows", ring)
-    rng = np.random.default_rng(100 + threads + ring)
+    ctx.set_option("poa_cols", cols)
+    rng = np.random.default_rng(100 + threads + ring + cols)
     try:
         for it in range(40):
             seqs = _random_group(rng, it)
@@ -63,6 +65,7 @@ def test_alignment_pairs_bit_exact(ctx, oracle, threads, ring):
     finally:
         ctx.set_option("poa_threads", 512)
         ctx.set_option("ring_rows", 12)
+        ctx.set_option("poa_cols", 8)
 
 
 def test_frozen_cases_and_known_answers(ctx, golden_dir):
