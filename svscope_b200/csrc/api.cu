@@ -106,6 +106,8 @@ int svs_set_option(svs_ctx* ctx, const char* key, int64_t value) {
   if (k == "poa_threads") {
     if (value != 128 && value != 256 && value != 512) return fail(ctx, SVS_ERR_ARG, "poa_threads must be 128, 256 or 512");
     ctx->poa_threads = static_cast<int>(value);
+  } else if (k == "prune") {
+    ctx->prune = value != 0;
   } else if (k == "poa_cols") {
     if (value != 8 && value != 16) return fail(ctx, SVS_ERR_ARG, "poa_cols must be 8 or 16");
     ctx->poa_cols = static_cast<int>(value);
@@ -145,6 +147,7 @@ int64_t svs_get_option(const svs_ctx* ctx, const char* key) {
   if (k == "poa_threads") return ctx->poa_threads;
   if (k == "ring_rows") return ctx->ring_rows;
   if (k == "poa_cols") return ctx->poa_cols;
+  if (k == "prune") return ctx->prune;
   if (k == "workers") return ctx->workers;
   if (k == "lane_jobs") return ctx->lane_jobs;
   if (k == "inflight") return ctx->inflight;

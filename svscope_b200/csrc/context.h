@@ -15,6 +15,7 @@ struct svs_ctx {
   std::string error;
   // options
   int poa_threads = 512;
+  int prune = 1;       // exact score-bound pruning of DP cells (persistent kernel)
   int poa_cols = 8;    // read columns per thread (16 only with 256 threads)
   int ring_rows = 12;
   int workers = 4;

@@ -51,7 +51,8 @@ struct TaskPlan {
   int64_t seq_id;
   uint32_t R, L, strip, npass, path_cap, w1, w2;
   uint64_t ldx;
-  size_t in_bytes, scratch_bytes, out_bytes, codes_bytes, xrows_bytes, bnd_bytes;
+  size_t in_bytes, scratch_bytes, out_bytes, codes_bytes, xrows_bytes, bnd_bytes, band_bytes;
+  bool prune;
   double cells;
 };
 
@@ -291,14 +292,19 @@ class Scheduler {
     tp->ldx = (static_cast<uint64_t>(tp->L) + 3 + C + 7) / 8 * 8;
     tp->path_cap = tp->R + tp->L + 2;
     const size_t R1 = static_cast<size_t>(g.R) + 1;
-    tp->in_bytes = align_up(R1, 16) * 2 /*letter, flags*/ + align_up((R1 + 1) * 4, 16) * 2 /*pred_off, single_before*/ +
+    tp->in_bytes = align_up(R1 * 16, 16) /*depth*/ +
+                   align_up(R1, 16) * 2 /*letter, flags*/ + align_up((R1 + 1) * 4, 16) * 2 /*pred_off, single_before*/ +
                    align_up(g.preds.size() * 4, 16) + align_up(R1 * 4, 16) * 3 /*xslot,h0,node_id*/ +
                    align_up(R1 * 2, 16);
     const size_t n1 = g.single_before[g.R + 1];
     tp->codes_bytes = align_up(n1 * tp->w1 + (static_cast<size_t>(tp->R) - n1) * tp->w2 + 64, 256);
     tp->xrows_bytes = align_up(static_cast<size_t>(g.n_export) * tp->ldx * 4, 256);
     tp->bnd_bytes = align_up(R1 * 4 * 8, 256);
-    tp->scratch_bytes = tp->codes_bytes + tp->xrows_bytes + tp->bnd_bytes;
+    tp->band_bytes = align_up(R1 * 8, 256);
+    tp->scratch_bytes = tp->codes_bytes + tp->xrows_bytes + tp->bnd_bytes + tp->band_bytes;
+    // exact pruning pays off on long alignments; scores must stay above -2^21 (kNegBand = -2^22)
+    tp->prune = ctx_->prune && tp->L >= 1024 && tp->R >= 1024 &&
+                worst * (static_cast<int64_t>(tp->R) + tp->L + 2) < (1 << 21);
     tp->out_bytes = align_up(16 + static_cast<size_t>(tp->path_cap) * 8, 16);
     tp->cells = (static_cast<double>(tp->R) + 1) * (static_cast<double>(tp->L) + 1);
     return true;
@@ -427,6 +433,7 @@ class Scheduler {
         off += align_up(bytes, 16);
         return dptr;
       };
+      t.depth = reinterpret_cast<const int32_t*>(put(g.depth.data(), R1 * 16));
       t.letter = put(g.letter.data(), R1);
       t.flags = put(g.flags.data(), R1);
       t.pred_off = reinterpret_cast<const uint32_t*>(put(g.pred_off.data(), (R1 + 1) * 4));
@@ -444,6 +451,9 @@ class Scheduler {
       t.off_codes = 0;
       t.off_xrows = tp.codes_bytes;
       t.off_bnd = tp.codes_bytes + tp.xrows_bytes;
+      t.off_band = tp.codes_bytes + tp.xrows_bytes + tp.bnd_bytes;
+      t.prune = (tp.prune && tp.scratch_bytes <= slot_bytes_) ? 1u : 0u;   // persistent path only
+      t.pad2_ = 0;
       if (tp.scratch_bytes > slot_bytes_) {
         uint8_t* base = d_big + big_offs[k];
         t.codes = base;

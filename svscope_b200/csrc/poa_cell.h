@@ -222,6 +222,28 @@ SVS_HD uint16_t row0_code(const Scores& s, int32_t j) {
   return make_code(kMoveHorz, ext, lcnext, 0, 0, 0);
 }
 
+// ---- exact pruning -----------------------------------------------------------------------------
+// Upper bound of the score of ANY global alignment through cell (row, j): the prefix consumes j
+// read characters and k1 graph nodes with dmin <= k1 <= dmax (nodes on a source->row path,
+// row included), the suffix L-j characters and k2 nodes with smin <= k2 <= smax (row->sink,
+// row excluded).  Each side scores at most m per aligned pair and at least |c| (the cheapest
+// gap character, no open charged so that a gap may straddle the cell) per unpaired one.
+// A cell with bound < score of some feasible alignment cannot lie on a co-optimal path, and
+// lowering such cells to "minus infinity" only lowers non-maximal candidates of the cells
+// that are, so every traceback decision is unchanged (DESIGN.md "Exact pruning").
+constexpr int32_t kNegBand = -(1 << 22);     // pruned cells; real scores stay above -2^21
+
+SVS_HD int32_t side_bound(const Scores& s, int32_t lo, int32_t hi, int32_t x) {
+  const int32_t k = x < lo ? lo : (x > hi ? hi : x);
+  const int32_t d = k > x ? k - x : x - k;
+  return s.m * (k < x ? k : x) + s.c * d;
+}
+
+SVS_HD int32_t cell_bound(const Scores& s, int32_t dmin, int32_t dmax, int32_t smin, int32_t smax, int32_t j,
+                          int32_t L) {
+  return side_bound(s, dmin, dmax, j) + side_bound(s, smin, smax, L - j);
+}
+
 // Everything the traceback needs to read.
 struct TbView {
   const uint8_t* codes;

@@ -256,6 +256,29 @@ void PoaGraph::export_ranked(const PoaScoring& sc, uint32_t ring_rows, RankedGra
   }
   out->single_before[R + 1] = singles;
   out->n_export = slot;
+  // path-length intervals used by the pruning bounds (poa_cell.h cell_bound)
+  out->depth.assign(4 * (static_cast<size_t>(R) + 1), 0);
+  int32_t* dp = out->depth.data();
+  for (uint32_t i = 1; i <= R; ++i) {
+    int32_t lo = INT32_MAX, hi = 0;
+    for (uint32_t k = out->pred_off[i]; k < out->pred_off[i + 1]; ++k) {
+      const uint32_t p = out->preds[k];
+      lo = std::min(lo, dp[4 * p]);
+      hi = std::max(hi, dp[4 * p + 1]);
+    }
+    dp[4 * i] = lo + 1;
+    dp[4 * i + 1] = hi + 1;
+  }
+  std::vector<uint8_t> seen(R + 1, 0);
+  for (uint32_t i = R; i >= 1; --i) {
+    for (uint32_t k = out->pred_off[i]; k < out->pred_off[i + 1]; ++k) {
+      const uint32_t p = out->preds[k];
+      if (p == 0) continue;
+      const int32_t a = dp[4 * i + 2] + 1, b = dp[4 * i + 3] + 1;
+      if (!seen[p]) { dp[4 * p + 2] = a; dp[4 * p + 3] = b; seen[p] = 1; }
+      else { dp[4 * p + 2] = std::min(dp[4 * p + 2], a); dp[4 * p + 3] = std::max(dp[4 * p + 3], b); }
+    }
+  }
 }
 
 std::vector<std::string> PoaGraph::msa() const {

@@ -31,6 +31,7 @@ struct RankedGraph {
   std::vector<uint16_t> col0code;  // [R+1] traceback code of column 0
   std::vector<uint32_t> node_id;   // [R+1]
   std::vector<uint32_t> single_before;  // [R+2] single-predecessor rows among rows 1..i-1
+  std::vector<int32_t> depth;      // [R+1][4] dmin, dmax (source->row, inclusive), smin, smax (row->sink, exclusive)
   uint32_t n_export = 0;
   uint32_t max_indeg = 0;
 };

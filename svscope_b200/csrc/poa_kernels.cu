@@ -49,16 +49,48 @@ struct Stage {
   int32_t pbh[kPredCap];
   int32_t xslot[kRowBatch];
   uint32_t single_before[kRowBatch];
+  int16_t tlo[kRowBatch], thi[kRowBatch];   // active thread range of the row in this strip (empty: tlo > thi)
+  int16_t ptlo[kPredCap], pthi[kPredCap];   // the same for every staged predecessor row
   int32_t bA[kRowBatch], bE[kRowBatch], bQ[kRowBatch];
   uint8_t letter[kRowBatch];
   uint8_t flags[kRowBatch];
 };
 
 // The dynamic programme of one alignment, executed by the whole CTA.
-template <int T, int kC>
+// Band of a row = the read columns that are computed; everything outside counts as minus
+// infinity (kNegBand).  MODE kFull: bands from `band` ([row][lo,hi], nullptr = all columns) and
+// traceback codes are produced.  MODE kScout: score only, narrow band around the depth
+// interval of the row (first pass of the exact pruning, see poa_cell.h).
+constexpr int kFull = 0, kScout = 1;
+constexpr int kScoutHalfWidth = 192;
+
+template <int MODE>
+__device__ __forceinline__ void row_band(const PoaTask& tk, const int32_t* band, uint32_t row, int32_t& lo, int32_t& hi) {
+  if (MODE == kScout) {
+    const int4 d = __ldg(reinterpret_cast<const int4*>(tk.depth) + row);
+    lo = max(1, d.x - kScoutHalfWidth);
+    hi = min(static_cast<int32_t>(tk.L), d.y + kScoutHalfWidth);
+  } else if (band != nullptr) {
+    const int2 b = __ldcg(reinterpret_cast<const int2*>(band) + row);
+    lo = b.x; hi = b.y;
+  } else {
+    lo = 1; hi = static_cast<int32_t>(tk.L);
+  }
+}
+
+// thread range [tlo, thi] of a band inside the strip [jb, je] (kC columns per thread)
+template <int kC>
+__device__ __forceinline__ void strip_threads(int32_t lo, int32_t hi, int32_t jb, int32_t je, int16_t& tlo, int16_t& thi) {
+  if (lo > hi || hi < jb || lo > je) { tlo = 1; thi = 0; return; }
+  tlo = static_cast<int16_t>((max(lo, jb) - jb) / kC);
+  thi = static_cast<int16_t>((min(hi, je) - jb) / kC);
+}
+
+template <int T, int kC, int MODE>
 __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, const SingleTables& tabs,
-                                         const int ring_rows, unsigned char* smem_raw) {
+                                         const int ring_rows, unsigned char* smem_raw, const int32_t* band) {
   static_assert(kC == 8 || kC == 16, "columns per thread");
+  const int32_t NEGW = pack_cell(kNegBand, kNeg, kNeg);
   constexpr int NW = T / 32;
   constexpr int WC = T * kC;
   int32_t* ring = reinterpret_cast<int32_t*>(smem_raw);
@@ -105,14 +137,24 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
         st.flags[tid] = tk.flags[i];
         st.xslot[tid] = tk.xslot[i];
         st.single_before[tid] = tk.single_before[i];
+        int32_t blo, bhi;
+        row_band<MODE>(tk, band, i, blo, bhi);
+        strip_threads<kC>(blo, bhi, static_cast<int32_t>(jb), static_cast<int32_t>(je), st.tlo[tid], st.thi[tid]);
+        // the row's own left boundary: column 0 (exact) in the first strip, else the last
+        // chunk of the previous strip if the band covered it
+        const bool own_left = (pass == 0) || (blo <= static_cast<int32_t>(jb) - 1 && bhi >= static_cast<int32_t>(jb) - kC);
         if (pass == 0) {
           st.bA[tid] = tk.h0[i];
           st.bE[tid] = kNeg;
           st.bQ[tid] = kNeg;
-        } else {
+        } else if (own_left) {
           st.bA[tid] = __ldcg(bin + bstride + i);
           st.bE[tid] = __ldcg(bin + 2 * bstride + i);
           st.bQ[tid] = __ldcg(bin + 3 * bstride + i);
+        } else {
+          st.bA[tid] = kNegBand;
+          st.bE[tid] = kNeg;
+          st.bQ[tid] = kNeg;
         }
         const uint32_t base = tk.pred_off[i0];
         const uint32_t pb = tk.pred_off[i], pe = tk.pred_off[i + 1];
@@ -121,17 +163,24 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
         for (uint32_t e = pb; e < pe; ++e) {
           const uint32_t p = tk.preds[e];
           int32_t src, bh;
+          int16_t ptlo = 0, pthi = static_cast<int16_t>(T);
           if (p == 0) {
             src = kSrcRow0;
             bh = row0_h(s, static_cast<int32_t>(jb) - 1);
           } else {
-            bh = (pass == 0) ? tk.h0[p] : __ldcg(bin + p);
+            int32_t plo, phi;
+            row_band<MODE>(tk, band, p, plo, phi);
+            strip_threads<kC>(plo, phi, static_cast<int32_t>(jb), static_cast<int32_t>(je), ptlo, pthi);
+            const bool p_left = (pass == 0) || (plo <= static_cast<int32_t>(jb) - 1 && phi >= static_cast<int32_t>(jb) - kC);
+            bh = (pass == 0) ? tk.h0[p] : (p_left ? __ldcg(bin + p) : kNegBand);
             if (p + 1 == i) src = kSrcAdj;
             else if (i - p <= static_cast<uint32_t>(ring_rows)) src = static_cast<int32_t>(p % ring_rows);
             else src = kSrcGlobal | tk.xslot[p];
           }
           st.psrc[e - base] = src;
           st.pbh[e - base] = bh;
+          st.ptlo[e - base] = ptlo;
+          st.pthi[e - base] = pthi;
         }
       }
       __syncthreads();
@@ -141,20 +190,37 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
         const uint32_t nb = st.poff[r], ne = st.poff[r + 1];
         const int32_t letter = st.letter[r];
         const bool single = (ne - nb == 1);
+        if (st.tlo[r] > st.thi[r]) {   // the row has no cell in this strip (uniform)
+          slot = (slot + 1 == static_cast<uint32_t>(ring_rows)) ? 0 : slot + 1;
+          continue;
+        }
+        const bool t_active = active && tid >= st.tlo[r] && tid <= st.thi[r];
         CellAcc acc[kC];
 #pragma unroll
         for (int c = 0; c < kC; ++c) { acc[c].Fm = 0; acc[c].Om = 0; acc[c].D = 0; acc[c].meta = 0; }
 
         // ---- phase 1: fold predecessor rows ------------------------------------------
-        if (active) {
+        if (t_active) {
           for (uint32_t e = nb; e < ne; ++e) {
             const int32_t src = st.psrc[e];
+            // cells of the predecessor row outside ITS band are minus infinity
+            const bool chunk_ok = tid >= st.ptlo[e] && tid <= st.pthi[e];
+            const bool left_ok = tid - 1 >= st.ptlo[e] && tid - 1 <= st.pthi[e];
             int32_t w[kC];
             int32_t hl;
-            if (src == kSrcAdj) {
+            if (src != kSrcRow0 && !chunk_ok) {
+#pragma unroll
+              for (int c = 0; c < kC; ++c) w[c] = NEGW;
+              hl = (tid == 0) ? st.pbh[e] : kNegBand;
+              if (tid > 0 && left_ok) {
+                if (src == kSrcAdj) hl = hleft_adj;
+                else if (src & kSrcGlobal) hl = unpack_h(__ldcg(tk.xrows + static_cast<uint64_t>(src & ~kSrcGlobal) * tk.ldx + 3 + j0 - 1));
+                else hl = unpack_h(ring[static_cast<size_t>(src) * WC + kC * tid - 1]);
+              }
+            } else if (src == kSrcAdj) {
 #pragma unroll
               for (int c = 0; c < kC; ++c) w[c] = wprev[c];
-              hl = hleft_adj;
+              hl = (tid == 0) ? st.pbh[e] : (left_ok ? hleft_adj : kNegBand);
             } else if (src == kSrcRow0) {
 #pragma unroll
               for (int c = 0; c < kC; ++c) w[c] = pack_cell(row0_h(s, static_cast<int32_t>(j0) + c), kNeg, kNeg);
@@ -166,7 +232,8 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
                 const int4 v = __ldcg(reinterpret_cast<const int4*>(row + j0 + 4 * q));
                 w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
               }
-              hl = unpack_h(__ldcg(row + j0 - 1));
+              hl = (tid == 0 || left_ok) ? unpack_h(__ldcg(row + j0 - 1)) : kNegBand;
+              if (tid == 0) hl = st.pbh[e];
             } else {
               const int32_t* row = ring + static_cast<size_t>(src) * WC;
 #pragma unroll
@@ -174,7 +241,7 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
                 const int4 v = *reinterpret_cast<const int4*>(row + kC * tid + 4 * q);
                 w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
               }
-              hl = (tid == 0) ? st.pbh[e] : unpack_h(row[kC * tid - 1]);
+              hl = (tid == 0) ? st.pbh[e] : (left_ok ? unpack_h(row[kC * tid - 1]) : kNegBand);
             }
             if (single) {
 #pragma unroll
@@ -194,15 +261,17 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
         }
 
         // ---- scan: horizontal gap states across the row ----------------------------------
-        int32_t a7 = 0;
+        int32_t a7 = kNegBand;
         int32_t el = kNeg, ql = kNeg, eloc7 = kNeg, qloc7 = kNeg;
+        if (t_active) {
 #pragma unroll
-        for (int c = 0; c < kC; ++c) {
-          const int32_t A = single ? imax(acc[c].D, imax(acc[c].Fm, acc[c].Om))
-                                   : imax(key_value(acc[c].D), key_value(static_cast<int32_t>(acc[c].meta)));
-          if (c == kC - 1) { eloc7 = el; qloc7 = ql; a7 = A; }
-          el = imax(A + s.g, el + s.e);
-          ql = imax(A + s.q, ql + s.c);
+          for (int c = 0; c < kC; ++c) {
+            const int32_t A = single ? imax(acc[c].D, imax(acc[c].Fm, acc[c].Om))
+                                     : imax(key_value(acc[c].D), key_value(static_cast<int32_t>(acc[c].meta)));
+            if (c == kC - 1) { eloc7 = el; qloc7 = ql; a7 = imax(A, kNegBand); }
+            el = imax(A + s.g, el + s.e);
+            ql = imax(A + s.q, ql + s.c);
+          }
         }
         const int32_t bA = st.bA[r], bE = st.bE[r], bQ = st.bQ[r];
         int32_t ein0 = 0, qin0 = 0;
@@ -280,43 +349,47 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
         hleft_adj = cy.H;
 
         // ---- phase 2: H, traceback codes, packed row --------------------------------------
-        uint32_t cw[kC / 2];
-        int32_t hsel = INT32_MIN;
-        if (single) {
+        if (t_active) {
+          uint32_t cw[kC / 2];
+          int32_t hsel = INT32_MIN;
+          if (single) {
 #pragma unroll
-          for (int c = 0; c < kC; ++c) {
-            int32_t H;
-            const uint32_t cd = cell_finish_single(acc[c], cy, s, H);
-            wprev[c] = pack_cell(H, acc[c].Fm, acc[c].Om);
-            if (c & 1) cw[c >> 1] |= cd << 16; else cw[c >> 1] = cd;
-            if (c == c_end) hsel = H;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < kC; ++c) {
-            int32_t H, Fv, Ov;
-            const uint32_t cd = cell_finish_key(acc[c], cy, s, H, Fv, Ov);
-            wprev[c] = pack_cell(H, Fv, Ov);
-            if (c & 1) cw[c >> 1] |= cd << 16; else cw[c >> 1] = cd;
-            if (c == c_end) hsel = H;
-          }
-        }
-        if (active) {
-          const uint64_t n1 = st.single_before[r];
-          uint8_t* crow = tk.codes + n1 * tk.w1 + (static_cast<uint64_t>(i - 1) - n1) * tk.w2;
-          if (single) {  // single predecessor: low bytes only
-            uint32_t b[kC / 4];
-#pragma unroll
-            for (int q = 0; q < kC / 4; ++q)
-              b[q] = (cw[2 * q] & 0xffu) | ((cw[2 * q] >> 8) & 0xff00u) | ((cw[2 * q + 1] & 0xffu) << 16) |
-                     ((cw[2 * q + 1] & 0xff0000u) << 8);
-            if (kC == 8) *reinterpret_cast<uint2*>(crow + (j0 - 1)) = make_uint2(b[0], b[1]);
-            else *reinterpret_cast<uint4*>(crow + (j0 - 1)) = make_uint4(b[0], b[1], b[kC / 4 - 2], b[kC / 4 - 1]);
+            for (int c = 0; c < kC; ++c) {
+              int32_t H;
+              const uint32_t cd = cell_finish_single(acc[c], cy, s, H);
+              H = imax(H, kNegBand); cy.H = H; cy.A = imax(cy.A, kNegBand);   // pruned neighbours must not drift
+              wprev[c] = pack_cell(H, acc[c].Fm, acc[c].Om);
+              if (c & 1) cw[c >> 1] |= cd << 16; else cw[c >> 1] = cd;
+              if (c == c_end) hsel = H;
+            }
           } else {
 #pragma unroll
-            for (int q = 0; q < kC / 8; ++q)
-              *reinterpret_cast<uint4*>(crow + 2 * static_cast<uint64_t>(j0 - 1) + 16 * q) =
-                  make_uint4(cw[4 * q], cw[4 * q + 1], cw[4 * q + 2], cw[4 * q + 3]);
+            for (int c = 0; c < kC; ++c) {
+              int32_t H, Fv, Ov;
+              const uint32_t cd = cell_finish_key(acc[c], cy, s, H, Fv, Ov);
+              H = imax(H, kNegBand); cy.H = H; cy.A = imax(cy.A, kNegBand);
+              wprev[c] = pack_cell(H, Fv, Ov);
+              if (c & 1) cw[c >> 1] |= cd << 16; else cw[c >> 1] = cd;
+              if (c == c_end) hsel = H;
+            }
+          }
+          if (MODE == kFull) {
+            const uint64_t n1 = st.single_before[r];
+            uint8_t* crow = tk.codes + n1 * tk.w1 + (static_cast<uint64_t>(i - 1) - n1) * tk.w2;
+            if (single) {  // single predecessor: low bytes only
+              uint32_t b[kC / 4];
+#pragma unroll
+              for (int q = 0; q < kC / 4; ++q)
+                b[q] = (cw[2 * q] & 0xffu) | ((cw[2 * q] >> 8) & 0xff00u) | ((cw[2 * q + 1] & 0xffu) << 16) |
+                       ((cw[2 * q + 1] & 0xff0000u) << 8);
+              if (kC == 8) *reinterpret_cast<uint2*>(crow + (j0 - 1)) = make_uint2(b[0], b[1]);
+              else *reinterpret_cast<uint4*>(crow + (j0 - 1)) = make_uint4(b[0], b[1], b[kC / 4 - 2], b[kC / 4 - 1]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < kC / 8; ++q)
+                *reinterpret_cast<uint4*>(crow + 2 * static_cast<uint64_t>(j0 - 1) + 16 * q) =
+                    make_uint4(cw[4 * q], cw[4 * q + 1], cw[4 * q + 2], cw[4 * q + 3]);
+            }
           }
           int32_t* rrow = ring + static_cast<size_t>(slot) * WC + kC * tid;
 #pragma unroll
@@ -357,7 +430,42 @@ __global__ void __launch_bounds__(T, (kC == 16 ? 1 : 512 / T)) poa_dp_kernel(con
                                                             const SingleTables tabs, const int ring_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PoaTask tk = tasks[blockIdx.x];
-  dp_align<T, kC>(tk, s, tabs, ring_rows, smem_raw);
+  dp_align<T, kC, kFull>(tk, s, tabs, ring_rows, smem_raw, nullptr);
+}
+
+// Band of every row for the exact second pass: the columns whose upper bound reaches the
+// score `lb` of the alignment found by the scout pass (cell_bound is concave in the column).
+template <int T>
+__device__ void compute_bands(const PoaTask& tk, const Scores& s, int32_t lb, bool have_lb, int32_t* band) {
+  const int32_t L = static_cast<int32_t>(tk.L);
+  for (uint32_t i = 1 + threadIdx.x; i <= tk.R; i += T) {
+    int32_t lo = 1, hi = L;
+    if (have_lb) {
+      const int4 d = __ldg(reinterpret_cast<const int4*>(tk.depth) + i);
+      auto ub = [&](int32_t j) { return cell_bound(s, d.x, d.y, d.z, d.w, j, L); };
+      // maximiser: one of the breakpoints of the two concave pieces
+      int32_t cand[6] = {1, L, d.x, d.y, L - d.w, L - d.z};
+      int32_t jm = 1, best = INT32_MIN;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int32_t j = min(L, max(1, cand[k]));
+        const int32_t v = ub(j);
+        if (v > best) { best = v; jm = j; }
+      }
+      if (best < lb) {
+        lo = 1; hi = 0;  // no cell of this row can be on a co-optimal path
+      } else {
+        int32_t a = 1, b = jm;      // first column with ub >= lb
+        while (a < b) { const int32_t mid = (a + b) >> 1; if (ub(mid) >= lb) b = mid; else a = mid + 1; }
+        lo = a;
+        a = jm; b = L;              // last column with ub >= lb
+        while (a < b) { const int32_t mid = (a + b + 1) >> 1; if (ub(mid) >= lb) a = mid; else b = mid - 1; }
+        hi = a;
+      }
+    }
+    band[2 * i] = lo;
+    band[2 * i + 1] = hi;
+  }
 }
 
 // Traceback by one warp.  Long diagonal runs through chain rows (one predecessor = the
@@ -432,7 +540,21 @@ __global__ void __launch_bounds__(T, 1) poa_persistent_kernel(const PoaTask* __r
     tk.codes = slot + tk.off_codes;
     tk.xrows = reinterpret_cast<int32_t*>(slot + tk.off_xrows);
     tk.bnd = reinterpret_cast<int32_t*>(slot + tk.off_bnd);
-    dp_align<T, kC>(tk, s, tabs, ring_rows, smem_raw);
+    int32_t* band = nullptr;
+    if (tk.prune) {
+      // exact pruning: scout pass in a narrow band -> score of a feasible alignment -> provable band
+      band = reinterpret_cast<int32_t*>(slot + tk.off_band);
+      if (threadIdx.x == 0) { tk.result[0] = 0; tk.result[1] = INT32_MIN; }
+      __syncthreads();
+      dp_align<T, kC, kScout>(tk, s, tabs, ring_rows, smem_raw, nullptr);
+      const bool have_lb = tk.result[0] > 0;
+      const int32_t lb = tk.result[1];
+      compute_bands<T>(tk, s, lb, have_lb, band);
+      __syncthreads();
+      if (threadIdx.x == 0) { tk.result[0] = 0; tk.result[1] = INT32_MIN; }
+      __syncthreads();
+    }
+    dp_align<T, kC, kFull>(tk, s, tabs, ring_rows, smem_raw, band);
     if (threadIdx.x < 32) tb_walk_warp(tk, s);
   }
 }

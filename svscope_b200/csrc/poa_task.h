@@ -17,6 +17,8 @@ struct PoaTask {
   const uint16_t* col0code;   // [R+1] traceback codes of column 0
   const uint32_t* node_id;    // [R+1]
   const uint32_t* single_before;  // [R+2] number of single-predecessor rows among rows 1..i-1
+  const int32_t* depth;       // [R+1][4] nodes on source->row paths (min, max; row included) and on
+                              // row->sink paths (min, max; row excluded): bounds of the exact pruning
   const uint8_t* read;        // [L]
   uint32_t R, L;
   uint32_t strip, npass;      // columns per pass (multiple of 8), number of passes
@@ -35,7 +37,9 @@ struct PoaTask {
   uint32_t path_cap;
   uint32_t pad_;
   // persistent kernel: scratch offsets inside the per-SM slot (codes/xrows/bnd are patched)
-  uint64_t off_codes, off_xrows, off_bnd;
+  uint64_t off_codes, off_xrows, off_bnd, off_band;
+  uint32_t prune;             // 1: scout pass + provable band before the full pass
+  uint32_t pad2_;
 };
 
 }  // namespace svs

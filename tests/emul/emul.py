@@ -38,13 +38,21 @@ def lib():
         L.emu_consensus.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
         L.emu_msa_dims.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.emu_msa.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.emu_set_prune.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.emu_kept_fraction.restype = ctypes.c_double
+        L.emu_kept_fraction.argtypes = [ctypes.c_void_p]
         _lib = L
     return _lib
 
 
 class EmuSession:
-    def __init__(self, ring_rows=4):
+    def __init__(self, ring_rows=4, prune=0):
         self.h = lib().emu_new(ring_rows)
+        if prune:
+            lib().emu_set_prune(self.h, prune)
+
+    def kept_fraction(self):
+        return lib().emu_kept_fraction(self.h)
 
     def add(self, seq):
         b = seq.encode()

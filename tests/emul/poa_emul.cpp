@@ -14,6 +14,8 @@
 using namespace svs;
 
 struct Emu {
+  int prune = 0;         // 0 off, >0: half-width of the first (narrow) pass
+  double kept_cells = 0, all_cells = 0;
   PoaGraph graph;
   PoaScoring sc;
   uint32_t ring_rows = 4;
@@ -37,40 +39,91 @@ static void emu_align(Emu* E, const uint8_t* read, uint32_t L) {
   P[0] = pack_cell(0, kNeg, kNeg);
   for (uint32_t j = 1; j <= L; ++j) P[j] = pack_cell(row0_h(s, j), kNeg, kNeg);
   const SingleTables tabs = make_single_tables(s);
+  // depths for the pruning bounds
+  std::vector<int32_t> dmin(R + 1, 0), dmax(R + 1, 0), smin(R + 1, 0), smax(R + 1, 0);
+  std::vector<uint8_t> has_succ(R + 1, 0);
+  for (uint32_t i = 1; i <= R; ++i) {
+    int32_t lo = INT32_MAX, hi = 0;
+    for (uint32_t k = G.pred_off[i]; k < G.pred_off[i + 1]; ++k) {
+      const uint32_t p = G.preds[k];
+      lo = std::min(lo, dmin[p]); hi = std::max(hi, dmax[p]);
+    }
+    dmin[i] = lo + 1; dmax[i] = hi + 1;
+  }
+  for (uint32_t i = R; i >= 1; --i) {
+    if (!has_succ[i]) { smin[i] = 0; smax[i] = 0; }
+    for (uint32_t k = G.pred_off[i]; k < G.pred_off[i + 1]; ++k) {
+      const uint32_t p = G.preds[k];
+      if (p == 0) continue;
+      if (!has_succ[p]) { smin[p] = smin[i] + 1; smax[p] = smax[i] + 1; has_succ[p] = 1; }
+      else { smin[p] = std::min(smin[p], smin[i] + 1); smax[p] = std::max(smax[p], smax[i] + 1); }
+    }
+  }
   int32_t best = INT32_MIN;
   uint32_t best_row = 0;
-  for (uint32_t i = 1; i <= R; ++i) {
-    P[i * W] = pack_cell(G.h0[i], kNeg, kNeg);
-    RowCarry cy{G.h0[i], kNeg, kNeg, G.h0[i]};
-    for (uint32_t j = 1; j <= L; ++j) {
-      CellAcc a;
-      const int32_t sub = (G.letter[i] == read[j - 1]) ? s.m : s.n;
-      const bool single = (G.pred_off[i + 1] - G.pred_off[i] == 1);
-      int32_t H;
-      uint16_t cd;
-      if (single) {  // the kernels' fast path
-        const uint32_t p = G.preds[G.pred_off[i]];
-        cell_pred_single(a, P[p * W + j], unpack_h(P[p * W + j - 1]), sub, s, tabs);
-        cd = static_cast<uint16_t>(cell_finish_single(a, cy, s, H));
+  std::vector<int32_t> lo_col(R + 1, 1), hi_col(R + 1, static_cast<int32_t>(L));
+  const int n_pass = E->prune > 0 ? 2 : 1;
+  for (int pass = 0; pass < n_pass; ++pass) {
+    if (E->prune > 0) {
+      if (pass == 0) {
+        for (uint32_t i = 1; i <= R; ++i) { lo_col[i] = std::max(1, dmin[i] - E->prune); hi_col[i] = std::min<int32_t>(L, dmax[i] + E->prune); }
       } else {
-        for (uint32_t k = G.pred_off[i]; k < G.pred_off[i + 1]; ++k) {
-          const uint32_t p = G.preds[k];
-          cell_pred_key(a, k - G.pred_off[i], P[p * W + j], unpack_h(P[p * W + j - 1]), sub, s, tabs);
+        const int32_t LB = best;  // score of a feasible alignment (or INT32_MIN: keep everything)
+        for (uint32_t i = 1; i <= R; ++i) {
+          int32_t lo = L + 1, hi = 0;
+          for (int32_t j = 1; j <= static_cast<int32_t>(L); ++j) {
+            if (LB == INT32_MIN || cell_bound(s, dmin[i], dmax[i], smin[i], smax[i], j, L) >= LB) { lo = std::min(lo, j); hi = std::max(hi, j); }
+          }
+          lo_col[i] = lo; hi_col[i] = hi;
+          E->kept_cells += std::max(0, hi - lo + 1);
+          E->all_cells += L;
         }
-        int32_t Fo, Oo;
-        cd = cell_finish_key(a, cy, s, H, Fo, Oo);
-        a.Fm = Fo; a.Om = Oo;
       }
-      const uint64_t n1 = G.single_before[i];
-      uint8_t* crow = codes.data() + n1 * w1 + (static_cast<uint64_t>(i - 1) - n1) * w2;
-      if (single) crow[j - 1] = static_cast<uint8_t>(cd);
-      else reinterpret_cast<uint16_t*>(crow)[j - 1] = cd;
-      P[i * W + j] = pack_cell(H, a.Fm, a.Om);
     }
-    if ((G.flags[i] & kFlagSink) && cy.H > best) {
-      best = cy.H;
-      best_row = i;
+    best = INT32_MIN; best_row = 0;
+    const int32_t NEGW = pack_cell(kNegBand, kNeg, kNeg);
+    for (uint32_t i = 1; i <= R; ++i) {
+      const bool col0_in = true;  // column 0 is exact (host values)
+      (void)col0_in;
+      P[i * W] = pack_cell(G.h0[i], kNeg, kNeg);
+      RowCarry cy{G.h0[i], kNeg, kNeg, G.h0[i]};
+      for (uint32_t j = 1; j <= L; ++j) {
+        if (E->prune > 0 && (static_cast<int32_t>(j) < lo_col[i] || static_cast<int32_t>(j) > hi_col[i])) {
+          P[i * W + j] = NEGW;
+          cy = RowCarry{kNegBand, kNeg, kNeg, kNegBand};
+          continue;
+        }
+        CellAcc a;
+        const int32_t sub = (G.letter[i] == read[j - 1]) ? s.m : s.n;
+        const bool single = (G.pred_off[i + 1] - G.pred_off[i] == 1);
+        int32_t H;
+        uint16_t cd;
+        if (single) {  // the kernels' fast path
+          const uint32_t p = G.preds[G.pred_off[i]];
+          cell_pred_single(a, P[p * W + j], unpack_h(P[p * W + j - 1]), sub, s, tabs);
+          cd = static_cast<uint16_t>(cell_finish_single(a, cy, s, H));
+        } else {
+          for (uint32_t k = G.pred_off[i]; k < G.pred_off[i + 1]; ++k) {
+            const uint32_t p = G.preds[k];
+            cell_pred_key(a, k - G.pred_off[i], P[p * W + j], unpack_h(P[p * W + j - 1]), sub, s, tabs);
+          }
+          int32_t Fo, Oo;
+          cd = cell_finish_key(a, cy, s, H, Fo, Oo);
+          a.Fm = Fo; a.Om = Oo;
+        }
+        if (E->prune > 0 && H < kNegBand) { H = kNegBand; cy.H = H; cy.A = std::max(cy.A, kNegBand); }
+        const uint64_t n1 = G.single_before[i];
+        uint8_t* crow = codes.data() + n1 * w1 + (static_cast<uint64_t>(i - 1) - n1) * w2;
+        if (single) crow[j - 1] = static_cast<uint8_t>(cd);
+        else reinterpret_cast<uint16_t*>(crow)[j - 1] = cd;
+        P[i * W + j] = pack_cell(H, std::max(a.Fm, kNegBand - 16), std::max(a.Om, kNegBand - 16));
+      }
+      if ((G.flags[i] & kFlagSink) && cy.H > best && (E->prune == 0 || hi_col[i] >= static_cast<int32_t>(L))) {
+        best = cy.H;
+        best_row = i;
+      }
     }
+    if (E->prune > 0 && pass == 0 && (best_row == 0 || best <= kNegBand + (1 << 20))) best = INT32_MIN;  // no feasible path in the narrow band
   }
   std::vector<int32_t> rev(2 * (static_cast<uint64_t>(R) + L + 2));
   const int32_t n = traceback_walk(best_row, L, codes.data(), w1, w2, G.single_before.data(), G.col0code.data(), G.pred_off.data(),
@@ -88,6 +141,8 @@ void* emu_new(int ring_rows) {
   e->ring_rows = ring_rows;
   return e;
 }
+void emu_set_prune(void* h, int half_width) { static_cast<Emu*>(h)->prune = half_width; }
+double emu_kept_fraction(void* h) { Emu* e = static_cast<Emu*>(h); return e->all_cells > 0 ? e->kept_cells / e->all_cells : 1.0; }
 void emu_free(void* h) { delete static_cast<Emu*>(h); }
 int64_t emu_add(void* h, const uint8_t* seq, int64_t len) {
   Emu* e = static_cast<Emu*>(h);

@@ -132,3 +132,37 @@ def test_high_indegree_and_long_gaps(ctx, oracle):
     for a, b in zip(ref, got):
         assert np.array_equal(a, b)
     assert max(o.graph()["indeg"]) >= 5
+
+
+def test_exact_pruning_equals_unpruned_and_oracle(ctx, oracle):
+    """Score-bound pruning (scout pass + provable band) must not change a single alignment:
+    pruned == unpruned on long windows (DEL, INS, tandem repeat, an unrelated read that makes
+    the scout pass fail), and == the oracle where the oracle is affordable."""
+    from svscope_b200._lib import ReadSet
+    from svscope_b200.poa_api import poa_groups
+    rng = np.random.default_rng(17)
+    wins = [synth.make_small_window(70, body_len=1400, sv_len=300, n_tumor=6, n_normal=6, n_carriers=3),
+            synth.make_small_window(71, body_len=2600, sv_len=700, n_tumor=6, n_normal=6, n_carriers=3, sv_type="INS"),
+            synth.make_c3(seed=7, total_len=3000, n_tumor=6, n_normal=6, n_carriers=3),
+            synth.make_small_window(72, body_len=5200, sv_len=1500, n_tumor=5, n_normal=5, n_carriers=3, sv_type="DEL"),
+            synth.make_small_window(73, body_len=6000, sv_len=900, n_tumor=5, n_normal=5, n_carriers=2, sv_type="INS", err=0.12)]
+    wins[0][0][4] = synth._to_str(synth._rand_seq(rng, 1500))      # unrelated read: no path in the narrow band
+    wins[1][0][3] = wins[1][0][3][:1100]                           # truncated read
+    seqs, groups = [], []
+    for w in wins:
+        groups.append(list(range(len(seqs), len(seqs) + len(w[0]))))
+        seqs += w[0]
+    reads = ReadSet(ctx, seqs)
+    try:
+        ctx.set_option("prune", 1)
+        cons1, msa1, st1 = poa_groups(ctx, reads, groups)
+        ctx.set_option("prune", 0)
+        cons0, msa0, st0 = poa_groups(ctx, reads, groups)
+    finally:
+        ctx.set_option("prune", 1)
+    assert cons1 == cons0
+    assert msa1 == msa0
+    for w, c, m in zip(wins[:3], cons1, msa1):
+        oc, om = oracle.poa(w[0], 1)
+        assert c == oc and m == om
+    reads.close()
