@@ -51,6 +51,7 @@ struct Stage {
   uint32_t single_before[kRowBatch];
   int16_t tlo[kRowBatch], thi[kRowBatch];   // active thread range of the row in this strip (empty: tlo > thi)
   int16_t ptlo[kPredCap], pthi[kPredCap];   // the same for every staged predecessor row
+  int wlo, whi;                             // warps that own a band cell of some row of the batch (empty: wlo > whi)
   int32_t bA[kRowBatch], bE[kRowBatch], bQ[kRowBatch];
   uint8_t letter[kRowBatch];
   uint8_t flags[kRowBatch];
@@ -184,6 +185,23 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
         }
       }
       __syncthreads();
+      if (tid == 0) {  // warps touched by the bands of this batch (bands are intervals => a contiguous range)
+        int lo_t = T, hi_t = -1;
+        for (uint32_t r = 0; r < nrows; ++r) {
+          if (st.tlo[r] <= st.thi[r]) { lo_t = min(lo_t, static_cast<int>(st.tlo[r])); hi_t = max(hi_t, static_cast<int>(st.thi[r])); }
+        }
+        st.wlo = lo_t >> 5;
+        st.whi = hi_t < 0 ? -1 : (hi_t >> 5);
+      }
+      __syncthreads();
+      const int wlo = st.wlo, whi = st.whi;
+      const int bar_threads = (whi - wlo + 1) * 32;
+      // warps outside the range own no band cell in any row of the batch: they skip it; the
+      // others synchronise among themselves with a named barrier
+      if (warp < wlo || warp > whi) {
+        for (uint32_t r = 0; r < nrows; ++r) slot = (slot + 1 == static_cast<uint32_t>(ring_rows)) ? 0 : slot + 1;
+        continue;
+      }
 
       for (uint32_t r = 0; r < nrows; ++r) {
         const uint32_t i = i0 + r;
@@ -303,10 +321,10 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
             pub[par * NW + warp] = pb;
           }
         }
-        __syncthreads();
+        asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
         int32_t t1e = kNeg, t1q = kNeg, t2e = kNeg, t2q = kNeg;
-        if (warp > 0) {
-          if (lane < warp) {
+        if (warp > wlo) {
+          if (lane < warp && lane >= wlo) {
             const WarpPub pb = pub[par * NW + lane];
             const int d1 = warp - 1 - lane;
             t1e = pb.e31 + 32 * kC * s.e * d1;
@@ -336,6 +354,8 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
         if (lane == 0) {
           if (warp == 0) {
             cy.A = bA; cy.E = bE; cy.Q = bQ;
+          } else if (warp == wlo) {   // everything to the left is outside every band of the batch
+            cy.A = kNegBand; cy.E = kNeg; cy.Q = kNeg;
           } else {
             const WarpPub pb = pub[par * NW + warp - 1];
             const int32_t einl = imax(pb.e30, t2e + kC * s.e * 31);
