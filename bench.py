@@ -349,6 +349,7 @@ def main():
         "wall_s_timed": wall, "gen_s": t_gen,
         "poa": {"cells_per_step": st["poa_cells"], "alignments_per_step": st["poa_alignments"],
                 "exported_row_frac": st["poa_exported_rows"] / max(1.0, st["poa_rows"]),
+                "pruning_retries_per_step": st.get("poa_prune_retries", 0.0),
                 "host_ms_per_step": {k: st.get("poa_" + k, 0.0) for k in
                                      ("host_wait_ms", "host_merge_ms", "host_plan_ms", "host_pack_ms", "launch_ms")}},
         "edit_distance": {"cells_per_step": st["ed_cells"], "kernel_ms_per_step": st["ed_ms"],
@@ -362,6 +363,15 @@ def main():
                                 "note": "CPU restatement of pyspoa (real pyspoa 0.2.1 SIMD engine unavailable offline) + "
                                         "numpy port of ReadsCluster/DecisionMaker + bit-parallel Levenshtein"}
     print(json.dumps(line))
+
+
+def _shutdown():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 def main_reference(args):
@@ -394,4 +404,7 @@ def main_reference(args):
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        _shutdown()

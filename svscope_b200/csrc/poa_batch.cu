@@ -38,6 +38,7 @@ namespace {
 struct PoaJob {
   int64_t group = 0;
   bool done = false;
+  double score_per_base = 4.0;   // of the last alignment (drives the pruning guess)
   std::vector<int64_t> seq_ids;
   size_t next = 0;
   PoaGraph graph;
@@ -60,7 +61,8 @@ struct WorkerStats {
   double cells = 0, alignments = 0, dp_ms = 0, tb_ms = 0, dp_launches = 0, tb_launches = 0,
          h2d = 0, d2h = 0, algo_bytes = 0, exported_rows = 0, rows = 0,
          host_wait_ms = 0, host_merge_ms = 0, host_plan_ms = 0, host_pack_ms = 0,
-         refill_ms = 0, starved = 0, launch_ms = 0, final_ms = 0, inflight_ms = 0, h2d_ms = 0, d2h_ms = 0;
+         refill_ms = 0, starved = 0, launch_ms = 0, final_ms = 0, inflight_ms = 0, h2d_ms = 0, d2h_ms = 0,
+         prune_retries = 0;
 };
 
 inline double now_ms() {
@@ -453,7 +455,8 @@ class Scheduler {
       t.off_bnd = tp.codes_bytes + tp.xrows_bytes;
       t.off_band = tp.codes_bytes + tp.xrows_bytes + tp.bnd_bytes;
       t.prune = (tp.prune && tp.scratch_bytes <= slot_bytes_) ? 1u : 0u;   // persistent path only
-      t.pad2_ = 0;
+      // guess: score per read base of the previous alignment of this graph, minus a margin
+      t.lb_guess = static_cast<int32_t>((tp.job->score_per_base - 0.10) * static_cast<double>(tp.L)) - 40;
       if (tp.scratch_bytes > slot_bytes_) {
         uint8_t* base = d_big + big_offs[k];
         t.codes = base;
@@ -516,6 +519,7 @@ class Scheduler {
     stats.h2d += st.in_bytes; stats.d2h += st.out_bytes;
     stats.alignments += n;
     std::vector<double> path_pairs(n, 0.0);
+    std::vector<int32_t> retries(n, 0);
     parallel_for(n, threads_, [&](int k) {
       const TaskPlan& tp = st.inflight[k];
       const int32_t* res = reinterpret_cast<const int32_t*>(st.h_out + st.out_offs[k]);
@@ -532,6 +536,8 @@ class Scheduler {
       }
       path_pairs[k] = np;
       PoaJob* job = tp.job;
+      job->score_per_base = static_cast<double>(res[1]) / std::max<uint32_t>(1, tp.L);
+      retries[k] = res[3];
       if (job->record) {
         std::vector<int32_t> rec(2 * static_cast<size_t>(np));
         for (int32_t a = 0; a < np; ++a) { rec[2 * a] = nodes[a]; rec[2 * a + 1] = pos[a]; }
@@ -546,6 +552,7 @@ class Scheduler {
       }
     });
     for (double v : path_pairs) stats.algo_bytes += 8.0 * v;
+    for (int32_t v : retries) stats.prune_retries += v;
     blocks_.release(st.blk_off, st.blk_bytes);
     st.blk_bytes = 0;
     st.inflight.clear();
@@ -644,7 +651,7 @@ int svs_poa_batch(svs_ctx* ctx, const svs_reads* reads, const int64_t* members, 
   st[10] = ws.exported_rows; st[11] = ws.rows;
   st[12] = ws.host_wait_ms; st[13] = ws.host_merge_ms; st[14] = ws.host_plan_ms; st[15] = ws.host_pack_ms;
   st[16] = ws.refill_ms; st[17] = ws.starved; st[18] = ws.launch_ms; st[19] = ws.final_ms;
-  st[20] = ws.inflight_ms; st[21] = ws.h2d_ms; st[22] = ws.d2h_ms;
+  st[20] = ws.inflight_ms; st[21] = ws.h2d_ms; st[22] = ws.d2h_ms; st[23] = ws.prune_retries;
   *out = res;
   return SVS_OK;
 }

@@ -439,7 +439,6 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
     if (owns_end) {
       tk.result[0] = static_cast<int32_t>(best_row);
       tk.result[1] = best;
-      tk.result[3] = 0;
     }
     __syncthreads();
   }
@@ -560,21 +559,31 @@ __global__ void __launch_bounds__(T, 1) poa_persistent_kernel(const PoaTask* __r
     tk.codes = slot + tk.off_codes;
     tk.xrows = reinterpret_cast<int32_t*>(slot + tk.off_xrows);
     tk.bnd = reinterpret_cast<int32_t*>(slot + tk.off_bnd);
+    // Exact pruning with a guessed lower bound: bands from the bound "cell_bound >= lb" are valid
+    // whenever lb <= optimal score.  The host guesses lb from the previous alignment of the same
+    // graph; a result below the guess proves the guess was too high, and the pass is repeated
+    // with the score just found (feasible, hence a true lower bound) or without pruning.
     int32_t* band = nullptr;
+    if (threadIdx.x == 0) tk.result[3] = 0;
     if (tk.prune) {
-      // exact pruning: scout pass in a narrow band -> score of a feasible alignment -> provable band
       band = reinterpret_cast<int32_t*>(slot + tk.off_band);
-      if (threadIdx.x == 0) { tk.result[0] = 0; tk.result[1] = INT32_MIN; }
-      __syncthreads();
-      dp_align<T, kC, kScout>(tk, s, tabs, ring_rows, smem_raw, nullptr);
-      const bool have_lb = tk.result[0] > 0;
-      const int32_t lb = tk.result[1];
-      compute_bands<T>(tk, s, lb, have_lb, band);
-      __syncthreads();
-      if (threadIdx.x == 0) { tk.result[0] = 0; tk.result[1] = INT32_MIN; }
-      __syncthreads();
+      int32_t lb = tk.lb_guess;
+      bool have_lb = true;
+      for (int attempt = 0; attempt < 3; ++attempt) {
+        if (threadIdx.x == 0) { tk.result[0] = 0; tk.result[1] = INT32_MIN; }
+        compute_bands<T>(tk, s, lb, have_lb, band);
+        __syncthreads();
+        dp_align<T, kC, kFull>(tk, s, tabs, ring_rows, smem_raw, band);
+        const int32_t found_row = tk.result[0], found = tk.result[1];
+        if (!have_lb || (found_row > 0 && found >= lb)) break;   // consistent with the bound used
+        if (threadIdx.x == 0) atomicAdd(reinterpret_cast<int*>(tk.result + 3), 1);   // count the retry
+        have_lb = found_row > 0 && found > kNegBand / 2;
+        lb = found;
+        __syncthreads();
+      }
+    } else {
+      dp_align<T, kC, kFull>(tk, s, tabs, ring_rows, smem_raw, nullptr);
     }
-    dp_align<T, kC, kFull>(tk, s, tabs, ring_rows, smem_raw, band);
     if (threadIdx.x < 32) tb_walk_warp(tk, s);
   }
 }
@@ -587,6 +596,7 @@ __global__ void poa_tb_kernel(const PoaTask* __restrict__ tasks, const Scores s,
                                    tk.single_before, tk.col0code, tk.pred_off, tk.preds, tk.node_id, s, tk.path,
                                    static_cast<int32_t>(tk.path_cap));
   tk.result[2] = n;
+  tk.result[3] = 0;
 }
 
 }  // namespace

@@ -32,14 +32,14 @@ struct PoaTask {
   uint64_t ldx;
   int32_t* bnd;               // [2][4][R+1] strip boundary state (H, A, E, Q), ping-pong
   // results
-  int32_t* result;            // [4] best_row, best_score, n_pairs, status
+  int32_t* result;            // [4] best_row, best_score, n_pairs, pruning retries
   int32_t* path;              // [2*path_cap] alignment pairs in reverse order
   uint32_t path_cap;
   uint32_t pad_;
   // persistent kernel: scratch offsets inside the per-SM slot (codes/xrows/bnd are patched)
   uint64_t off_codes, off_xrows, off_bnd, off_band;
-  uint32_t prune;             // 1: scout pass + provable band before the full pass
-  uint32_t pad2_;
+  uint32_t prune;             // 1: prune with bands from `lb_guess` (retry inside the kernel if it was too high)
+  int32_t lb_guess;           // guessed lower bound of the optimal score
 };
 
 }  // namespace svs

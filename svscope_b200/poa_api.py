@@ -12,7 +12,7 @@ from ._lib import Context, ReadSet, c_vp, load, ptr
 STAT_NAMES = ["cells", "alignments", "dp_ms", "tb_ms", "wall_ms", "dp_launches", "tb_launches",
               "h2d_bytes", "d2h_bytes", "algo_bytes", "exported_rows", "rows", "host_wait_ms", "host_merge_ms",
               "host_plan_ms", "host_pack_ms", "refill_ms", "starved_polls", "launch_ms", "final_ms", "inflight_ms",
-              "h2d_ms", "d2h_ms"]
+              "h2d_ms", "d2h_ms", "prune_retries"]
 DEFAULT_SCORES = dict(m=5, n=-4, g=-8, e=-6, q=-10, c=-4)
 
 

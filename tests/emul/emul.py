@@ -39,6 +39,9 @@ def lib():
         L.emu_msa_dims.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.emu_msa.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.emu_set_prune.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.emu_set_dyn.argtypes = [ctypes.c_void_p, ctypes.c_double]
+        L.emu_retries.restype = ctypes.c_int
+        L.emu_retries.argtypes = [ctypes.c_void_p]
         L.emu_kept_fraction.restype = ctypes.c_double
         L.emu_kept_fraction.argtypes = [ctypes.c_void_p]
         _lib = L
@@ -46,10 +49,15 @@ def lib():
 
 
 class EmuSession:
-    def __init__(self, ring_rows=4, prune=0):
+    def __init__(self, ring_rows=4, prune=0, dyn=None):
         self.h = lib().emu_new(ring_rows)
         if prune:
             lib().emu_set_prune(self.h, prune)
+        if dyn is not None:
+            lib().emu_set_dyn(self.h, float(dyn))
+
+    def retries(self):
+        return lib().emu_retries(self.h)
 
     def kept_fraction(self):
         return lib().emu_kept_fraction(self.h)

@@ -15,6 +15,9 @@ using namespace svs;
 
 struct Emu {
   int prune = 0;         // 0 off, >0: half-width of the first (narrow) pass
+  int dyn = 0;           // 1: dynamic score-bound pruning with a guessed lower bound (lb_ratio * L)
+  double lb_ratio = 4.0;
+  int retries = 0;
   double kept_cells = 0, all_cells = 0;
   PoaGraph graph;
   PoaScoring sc;
@@ -23,10 +26,22 @@ struct Emu {
   RankedGraph rg;
 };
 
+static bool emu_align_dyn(Emu* E, const uint8_t* read, uint32_t L, int32_t lb, int32_t* score_out);
+
 static void emu_align(Emu* E, const uint8_t* read, uint32_t L) {
   E->last.clear();
   if (E->graph.empty() || L == 0) return;
   E->graph.export_ranked(E->sc, E->ring_rows, &E->rg);
+  if (E->dyn) {
+    int32_t lb = static_cast<int32_t>(E->lb_ratio * L), score = 0;
+    bool ok = emu_align_dyn(E, read, L, lb, &score);
+    if (!ok || score < lb) {   // the guess was above the optimum: repeat with a feasible score (or unpruned)
+      ++E->retries;
+      lb = ok ? score : INT32_MIN;
+      ok = emu_align_dyn(E, read, L, lb, &score);
+    }
+    return;
+  }
   const RankedGraph& G = E->rg;
   const Scores s{E->sc.m, E->sc.n, E->sc.g, E->sc.e, E->sc.q, E->sc.c};
   const uint32_t R = G.R;
@@ -135,6 +150,116 @@ static void emu_align(Emu* E, const uint8_t* read, uint32_t L) {
   }
 }
 
+// Dynamic exact pruning (emulation of the planned kernel scheme): a cell is RELEVANT when
+// H + suffix bound >= lb.  Row i computes the chunk interval [min rlo_p, max rhi_p + 1 + ext]
+// over its predecessors p (ext = provable maximum length of a relevant horizontal run), cells
+// outside are minus infinity; afterwards its own relevant interval is recorded.  lb is a guess;
+// when the result scores below the guess the pass is repeated with the found score.
+static bool emu_align_dyn(Emu* E, const uint8_t* read, uint32_t L, int32_t lb, int32_t* score_out) {
+  const RankedGraph& G = E->rg;
+  const Scores s{E->sc.m, E->sc.n, E->sc.g, E->sc.e, E->sc.q, E->sc.c};
+  const uint32_t R = G.R;
+  const uint64_t W = L + 1;
+  const int C = 8;
+  const SingleTables tabs = make_single_tables(s);
+  std::vector<int32_t> P((R + 1) * W, pack_cell(kNegBand, kNeg, kNeg));
+  const uint32_t w1 = (L + 7 + 15) / 16 * 16, w2 = (L + 7 + 7) / 8 * 8 * 2;
+  const uint64_t n1_total = G.single_before[R + 1];
+  static std::vector<uint8_t> codes;
+  codes.assign(n1_total * w1 + (R - n1_total) * w2 + 64, 0);
+  P[0] = pack_cell(0, kNeg, kNeg);
+  for (uint32_t j = 1; j <= L; ++j) P[j] = pack_cell(row0_h(s, j), kNeg, kNeg);
+  const int nchunk = (L + C - 1) / C;
+  std::vector<int> rlo(R + 1, nchunk), rhi(R + 1, -1);     // relevant chunk interval per row
+  std::vector<int> clo(R + 1, nchunk), chi(R + 1, -1);     // computed chunk interval per row
+  // row 0: everything is available (closed form)
+  rlo[0] = 0; rhi[0] = nchunk - 1; clo[0] = 0; chi[0] = nchunk - 1;
+  const bool have_lb = lb > INT32_MIN / 2;
+  int ext = nchunk;
+  if (have_lb) {
+    const int64_t slack = static_cast<int64_t>(s.m) * L - lb;
+    const int64_t dmax = slack <= 0 ? 0 : slack / (s.m - s.c) + 1;
+    ext = static_cast<int>(std::min<int64_t>(nchunk, dmax / C + 2));
+  }
+  int32_t best = INT32_MIN; uint32_t best_row = 0;
+  const int32_t* dp = G.depth.data();
+  for (uint32_t i = 1; i <= R; ++i) {
+    P[i * W] = pack_cell(G.h0[i], kNeg, kNeg);
+    int lo = nchunk, hi = -1;
+    for (uint32_t k = G.pred_off[i]; k < G.pred_off[i + 1]; ++k) {
+      const uint32_t p = G.preds[k];
+      if (rlo[p] <= rhi[p]) { lo = std::min(lo, rlo[p]); hi = std::max(hi, rhi[p] + 1); }
+    }
+    if (!have_lb) { lo = 0; hi = nchunk - 1; }
+    else if (lo <= hi) hi = std::min(nchunk - 1, hi + ext);
+    clo[i] = lo; chi[i] = hi;
+    if (lo > hi) continue;
+    RowCarry cy;
+    if (lo == 0) cy = RowCarry{G.h0[i], kNeg, kNeg, G.h0[i]};
+    else cy = RowCarry{kNegBand, kNeg, kNeg, kNegBand};
+    for (int t = lo; t <= hi; ++t) {
+      int32_t hmax = INT32_MIN;
+      for (int c = 0; c < C; ++c) {
+        const uint32_t j = 1 + t * C + c;
+        if (j > L) break;
+        CellAcc a;
+        const int32_t sub = (G.letter[i] == read[j - 1]) ? s.m : s.n;
+        const bool single = (G.pred_off[i + 1] - G.pred_off[i] == 1);
+        auto pw = [&](uint32_t p, uint32_t jj) -> int32_t {   // predecessor cell, minus infinity outside its computed interval
+          if (p == 0 || jj == 0) return P[p * W + jj];
+          const int tc = (static_cast<int>(jj) - 1) / C;
+          return (tc >= clo[p] && tc <= chi[p]) ? P[p * W + jj] : pack_cell(kNegBand, kNeg, kNeg);
+        };
+        int32_t H; uint16_t cd;
+        if (single) {
+          const uint32_t p = G.preds[G.pred_off[i]];
+          cell_pred_single(a, pw(p, j), unpack_h(pw(p, j - 1)), sub, s, tabs);
+          cd = static_cast<uint16_t>(cell_finish_single(a, cy, s, H));
+        } else {
+          for (uint32_t k = G.pred_off[i]; k < G.pred_off[i + 1]; ++k) {
+            const uint32_t p = G.preds[k];
+            cell_pred_key(a, k - G.pred_off[i], pw(p, j), unpack_h(pw(p, j - 1)), sub, s, tabs);
+          }
+          int32_t Fo, Oo;
+          cd = cell_finish_key(a, cy, s, H, Fo, Oo);
+          a.Fm = Fo; a.Om = Oo;
+        }
+        H = std::max(H, kNegBand); cy.H = H; cy.A = std::max(cy.A, kNegBand);
+        const uint64_t n1 = G.single_before[i];
+        uint8_t* crow = codes.data() + n1 * w1 + (static_cast<uint64_t>(i - 1) - n1) * w2;
+        if (single) crow[j - 1] = static_cast<uint8_t>(cd);
+        else reinterpret_cast<uint16_t*>(crow)[j - 1] = cd;
+        P[i * W + j] = pack_cell(H, a.Fm, a.Om);
+        hmax = std::max(hmax, H);
+        if (j == L && (G.flags[i] & kFlagSink) && H > best) { best = H; best_row = i; }
+      }
+      // chunk relevance: best H of the chunk + the largest suffix bound over its columns
+      bool rel = !have_lb;
+      if (have_lb) {
+        const int32_t ja = 1 + t * C, jb = std::min<int32_t>(L, ja + C - 1);
+        int32_t ub = INT32_MIN;
+        for (int32_t j = ja; j <= jb; ++j) ub = std::max(ub, side_bound(s, dp[4 * i + 2], dp[4 * i + 3], static_cast<int32_t>(L) - j));
+        rel = static_cast<int64_t>(hmax) + ub >= lb;
+      }
+      if (rel) { rlo[i] = std::min(rlo[i], t); rhi[i] = std::max(rhi[i], t); }
+      E->kept_cells += C;
+    }
+    E->all_cells += L;
+  }
+  *score_out = best;
+  if (best_row == 0) return false;
+  std::vector<int32_t> rev(2 * (static_cast<uint64_t>(R) + L + 2));
+  const int32_t n = traceback_walk(best_row, L, codes.data(), w1, w2, G.single_before.data(), G.col0code.data(), G.pred_off.data(),
+                                   G.preds.data(), G.node_id.data(), s, rev.data(),
+                                   static_cast<int32_t>(R + L + 2));
+  E->last.clear();
+  for (int32_t k = n - 1; k >= 0; --k) {
+    E->last.push_back(rev[2 * k]);
+    E->last.push_back(rev[2 * k + 1]);
+  }
+  return true;
+}
+
 extern "C" {
 void* emu_new(int ring_rows) {
   Emu* e = new Emu();
@@ -142,6 +267,8 @@ void* emu_new(int ring_rows) {
   return e;
 }
 void emu_set_prune(void* h, int half_width) { static_cast<Emu*>(h)->prune = half_width; }
+void emu_set_dyn(void* h, double lb_ratio) { static_cast<Emu*>(h)->dyn = 1; static_cast<Emu*>(h)->lb_ratio = lb_ratio; }
+int emu_retries(void* h) { return static_cast<Emu*>(h)->retries; }
 double emu_kept_fraction(void* h) { Emu* e = static_cast<Emu*>(h); return e->all_cells > 0 ? e->kept_cells / e->all_cells : 1.0; }
 void emu_free(void* h) { delete static_cast<Emu*>(h); }
 int64_t emu_add(void* h, const uint8_t* seq, int64_t len) {
