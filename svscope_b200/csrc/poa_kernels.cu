@@ -59,19 +59,13 @@ struct Stage {
 
 // The dynamic programme of one alignment, executed by the whole CTA.
 // Band of a row = the read columns that are computed; everything outside counts as minus
-// infinity (kNegBand).  MODE kFull: bands from `band` ([row][lo,hi], nullptr = all columns) and
-// traceback codes are produced.  MODE kScout: score only, narrow band around the depth
-// interval of the row (first pass of the exact pruning, see poa_cell.h).
-constexpr int kFull = 0, kScout = 1;
-constexpr int kScoutHalfWidth = 192;
+// infinity (kNegBand).  Bands come from `band` ([row][lo,hi]; nullptr = all columns), see
+// compute_bands and the "exact pruning" notes in poa_cell.h.
+constexpr int kFull = 0;
 
 template <int MODE>
 __device__ __forceinline__ void row_band(const PoaTask& tk, const int32_t* band, uint32_t row, int32_t& lo, int32_t& hi) {
-  if (MODE == kScout) {
-    const int4 d = __ldg(reinterpret_cast<const int4*>(tk.depth) + row);
-    lo = max(1, d.x - kScoutHalfWidth);
-    hi = min(static_cast<int32_t>(tk.L), d.y + kScoutHalfWidth);
-  } else if (band != nullptr) {
+  if (band != nullptr) {
     const int2 b = __ldcg(reinterpret_cast<const int2*>(band) + row);
     lo = b.x; hi = b.y;
   } else {
@@ -452,8 +446,8 @@ __global__ void __launch_bounds__(T, (kC == 16 ? 1 : 512 / T)) poa_dp_kernel(con
   dp_align<T, kC, kFull>(tk, s, tabs, ring_rows, smem_raw, nullptr);
 }
 
-// Band of every row for the exact second pass: the columns whose upper bound reaches the
-// score `lb` of the alignment found by the scout pass (cell_bound is concave in the column).
+// Band of every row: the columns whose upper bound (cell_bound, concave in the column) reaches
+// the lower bound `lb` of the optimal score.
 template <int T>
 __device__ void compute_bands(const PoaTask& tk, const Scores& s, int32_t lb, bool have_lb, int32_t* band) {
   const int32_t L = static_cast<int32_t>(tk.L);

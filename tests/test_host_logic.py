@@ -48,6 +48,33 @@ def test_emulated_kernel_path_equals_oracle(oracle):
         e.close()
 
 
+def test_pruned_emulation_equals_oracle(oracle):
+    """Exact pruning theory on CPU: cells whose score upper bound is below a feasible alignment
+    score are set to minus infinity (static bands from path-length intervals, and a dynamic
+    variant with a guessed bound and retry); every alignment must stay identical."""
+    from tests.emul.emul import EmuSession
+    rng = np.random.default_rng(23)
+    for it in range(60):
+        seqs = _random_group(rng, it)
+        if it % 5 == 0:
+            seqs[-1] = synth._to_str(synth._rand_seq(rng, int(rng.integers(1, 90))))   # unrelated read
+        kw = dict(prune=int(rng.choice([1, 8, 64]))) if it % 2 == 0 else dict(dyn=float(rng.choice([2.0, 4.2, 5.0])))
+        o, e = oracle.PoaSession(1), EmuSession(ring_rows=3, **kw)
+        for s in seqs:
+            assert np.array_equal(o.add(s), e.add(s))
+        assert o.msa() == e.msa() and o.consensus() == e.consensus()
+        o.close()
+        e.close()
+    w = synth.make_small_window(3, body_len=1200, sv_len=300, n_tumor=6, n_normal=6, n_carriers=3)
+    e = EmuSession(ring_rows=3, prune=32)
+    o = oracle.PoaSession(1)
+    for s in w[0]:
+        assert np.array_equal(o.add(s), e.add(s))
+    assert e.kept_fraction() < 0.6          # the bound really prunes
+    o.close()
+    e.close()
+
+
 def test_margin_columns_equals_reference_loop(oracle):
     rng = np.random.default_rng(0)
     for _ in range(2000):
