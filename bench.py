@@ -33,7 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before any CUDA context (see svscope_b200/__init__.py)
 
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 55.49e9   # profiles/r01_poa_persistent_kernel_ncu_full.txt
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 10.16e9   # profiles/r01_poa_persistent_kernel_pruned_ncu_full.txt (one launch, 148 alignments)
 METRIC = "localGraph windows/sec"
 UNIT = "windows/s"
 WORKLOAD = "configs[1]: synthetic INS/DEL windows, 30 tumor + 30 normal reads, 5-15 kb, 5% error"
@@ -314,10 +314,10 @@ def main():
     achieved_gbs = algo_bytes_per_launch / avg_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved_gbs / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (148 alignments, read 46 of the "
-                                "window-MSA stage) from profiles/r01_poa_persistent_kernel_ncu_full.txt; almost all of it is "
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (148 alignments, launch 21 of a depth-12 probe: "
+                                "profiles/r01_poa_persistent_kernel_pruned_ncu_full.txt); almost all of it is "
                                 "traceback codes (1-2 B per DP cell), which are implementation traffic, not algorithmic bytes",
-                "kernel": "poa_dp_kernel", "launches_per_step": n_launch,
+                "kernel": "poa_persistent_kernel<512,8>", "launches_per_step": n_launch,
                 "avg_launch_ms": avg_launch_s * 1e3,
                 "note": "algorithmic bytes = read + rank-ordered graph + alignment path (SURVEY 8d); the kernel is "
                         "integer-ALU bound, see roofline_alu; launches of different worker streams overlap, so the "
@@ -329,8 +329,9 @@ def main():
     peak_gcups = alu["addmax"] * 2.0 / ops_per_cell   # fused add+max counts as two algorithmic ops
     roofline_alu = {"bound": "int_alu", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": gcups / peak_gcups,
                     "probe_gops": alu, "ops_per_cell": ops_per_cell,
-                    "note": "cells = sum (|V|+1)(L+1) over alignments; achieved over the wall time of the two POA stages "
-                            "(last timed step); peak = measured fused add+max issue rate x 2 / 18 ops per cell"}
+                    "note": "NOMINAL cells = sum (|V|+1)(L+1) over alignments (what the CPU engine fills); exact pruning evaluates "
+                            "about 30 % of them; achieved over the wall time of the two POA stages (last timed step); "
+                            "peak = measured fused add+max issue rate x 2 / 18 ops per cell"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_max / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -15,7 +15,7 @@ if os.environ.get("C1"):
     depth = int(os.environ.get("DEPTH", 30))
     wins = [synth.make_c1(seed=s, n_tumor=depth, n_normal=depth, n_carriers=depth // 2) for s in range(1, nwin + 1)]
 else:
-    wins = synth.make_c2(nwin)
+    wins = synth.make_c2(nwin, depth=int(os.environ.get("DEPTH", 30)))
 print("gen", round(time.time() - t0, 1), "s; windows", len(wins), "mean len", np.mean([len(w[0][0]) for w in wins]), flush=True)
 reads = upload_windows(ctx, wins)
 for rep in range(int(os.environ.get("REPS", 1))):

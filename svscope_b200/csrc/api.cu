@@ -109,7 +109,7 @@ int svs_set_option(svs_ctx* ctx, const char* key, int64_t value) {
   } else if (k == "prune") {
     ctx->prune = value != 0;
   } else if (k == "poa_cols") {
-    if (value != 8 && value != 16) return fail(ctx, SVS_ERR_ARG, "poa_cols must be 8 or 16");
+    if (value != 4 && value != 8 && value != 16) return fail(ctx, SVS_ERR_ARG, "poa_cols must be 4, 8 or 16");
     ctx->poa_cols = static_cast<int>(value);
   } else if (k == "ring_rows") {
     if (value < 1 || value > 64) return fail(ctx, SVS_ERR_ARG, "ring_rows out of range");

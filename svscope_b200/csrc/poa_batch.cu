@@ -174,6 +174,7 @@ class Scheduler {
   int run(std::vector<PoaJob>& jobs) {
     const int njobs = static_cast<int>(jobs.size());
     threads_ = std::max(1, ctx_->workers);
+    if (const char* pm = getenv("SVS_PRUNE_MARGIN")) prune_margin_ = atof(pm);
     // Device arena: [per-SM scratch slots | blocks for graph arrays, paths and oversized alignments]
     n_sm_ = std::max(1, ctx_->sm_count);
     // persistent mode needs exactly one resident CTA per SM (512 threads, > 114 KB shared memory);
@@ -456,7 +457,7 @@ class Scheduler {
       t.off_band = tp.codes_bytes + tp.xrows_bytes + tp.bnd_bytes;
       t.prune = (tp.prune && tp.scratch_bytes <= slot_bytes_) ? 1u : 0u;   // persistent path only
       // guess: score per read base of the previous alignment of this graph, minus a margin
-      t.lb_guess = static_cast<int32_t>((tp.job->score_per_base - 0.10) * static_cast<double>(tp.L)) - 40;
+      t.lb_guess = static_cast<int32_t>((tp.job->score_per_base - prune_margin_) * static_cast<double>(tp.L)) - 40;
       if (tp.scratch_bytes > slot_bytes_) {
         uint8_t* base = d_big + big_offs[k];
         t.codes = base;
@@ -568,6 +569,7 @@ class Scheduler {
   int threads_ = 1, n_sm_ = 1, n_slots_ = 1;
   uint32_t cols_ = 8;
   bool persistent_ = false;
+  double prune_margin_ = 0.10;   // score per base subtracted from the previous alignment's rate
   size_t slot_bytes_ = 0, block_bytes_ = 0;
   uint8_t* slot_base_ = nullptr;
   uint8_t* block_base_ = nullptr;

@@ -84,7 +84,7 @@ __device__ __forceinline__ void strip_threads(int32_t lo, int32_t hi, int32_t jb
 template <int T, int kC, int MODE>
 __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, const SingleTables& tabs,
                                          const int ring_rows, unsigned char* smem_raw, const int32_t* band) {
-  static_assert(kC == 8 || kC == 16, "columns per thread");
+  static_assert(kC == 4 || kC == 8 || kC == 16, "columns per thread");
   const int32_t NEGW = pack_cell(kNegBand, kNeg, kNeg);
   constexpr int NW = T / 32;
   constexpr int WC = T * kC;
@@ -396,8 +396,11 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
               for (int q = 0; q < kC / 4; ++q)
                 b[q] = (cw[2 * q] & 0xffu) | ((cw[2 * q] >> 8) & 0xff00u) | ((cw[2 * q + 1] & 0xffu) << 16) |
                        ((cw[2 * q + 1] & 0xff0000u) << 8);
-              if (kC == 8) *reinterpret_cast<uint2*>(crow + (j0 - 1)) = make_uint2(b[0], b[1]);
+              if (kC == 4) *reinterpret_cast<uint32_t*>(crow + (j0 - 1)) = b[0];
+              else if (kC == 8) *reinterpret_cast<uint2*>(crow + (j0 - 1)) = make_uint2(b[0], b[kC / 4 - 1]);
               else *reinterpret_cast<uint4*>(crow + (j0 - 1)) = make_uint4(b[0], b[1], b[kC / 4 - 2], b[kC / 4 - 1]);
+            } else if (kC == 4) {
+              *reinterpret_cast<uint2*>(crow + 2 * static_cast<uint64_t>(j0 - 1)) = make_uint2(cw[0], cw[1]);
             } else {
 #pragma unroll
               for (int q = 0; q < kC / 8; ++q)
@@ -595,7 +598,11 @@ __global__ void poa_tb_kernel(const PoaTask* __restrict__ tasks, const Scores s,
 
 }  // namespace
 
-int poa_cols_per_thread(int threads, int cols) { return (cols == 16 && threads == 256) ? 16 : 8; }
+int poa_cols_per_thread(int threads, int cols) {
+  if (cols == 16 && threads == 256) return 16;
+  if (cols == 4 && threads == 512) return 4;
+  return 8;
+}
 
 size_t poa_dp_smem_bytes(int threads, int ring_rows, int cols) {
   return static_cast<size_t>(ring_rows) * threads * poa_cols_per_thread(threads, cols) * sizeof(int32_t) +
@@ -608,6 +615,8 @@ cudaError_t poa_dp_configure(int threads, int ring_rows, int cols) {
   const int bytes = static_cast<int>(poa_dp_smem_bytes(threads, ring_rows, cols));
   if (poa_cols_per_thread(threads, cols) == 16)
     return cudaFuncSetAttribute(poa_dp_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (poa_cols_per_thread(threads, cols) == 4)
+    return cudaFuncSetAttribute(poa_dp_kernel<512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   switch (threads) {
     case 128: return cudaFuncSetAttribute(poa_dp_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     case 256: return cudaFuncSetAttribute(poa_dp_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -625,6 +634,10 @@ cudaError_t poa_dp_launch(const PoaTask* d_tasks, int n_tasks, const Scores& s, 
     poa_dp_kernel<256, 16><<<n_tasks, 256, smem, stream>>>(d_tasks, s, tabs, ring_rows);
     return cudaGetLastError();
   }
+  if (poa_cols_per_thread(threads, cols) == 4) {
+    poa_dp_kernel<512, 4><<<n_tasks, 512, smem, stream>>>(d_tasks, s, tabs, ring_rows);
+    return cudaGetLastError();
+  }
   switch (threads) {
     case 128: poa_dp_kernel<128, 8><<<n_tasks, 128, smem, stream>>>(d_tasks, s, tabs, ring_rows); break;
     case 256: poa_dp_kernel<256, 8><<<n_tasks, 256, smem, stream>>>(d_tasks, s, tabs, ring_rows); break;
@@ -636,14 +649,15 @@ cudaError_t poa_dp_launch(const PoaTask* d_tasks, int n_tasks, const Scores& s, 
 
 // persistent mode needs exactly one resident CTA per SM: > 114 KB of shared memory
 bool poa_persistent_supported(int threads, int ring_rows, int cols) {
-  const bool shape = (threads == 512 && poa_cols_per_thread(threads, cols) == 8) ||
-                     (threads == 256 && poa_cols_per_thread(threads, cols) == 16);
+  const bool shape = threads == 512 || (threads == 256 && poa_cols_per_thread(threads, cols) == 16);
   return shape && poa_dp_smem_bytes(threads, ring_rows, cols) > 114 * 1024;
 }
 
 cudaError_t poa_persistent_configure(int threads, int ring_rows, int cols) {
   if (!poa_persistent_supported(threads, ring_rows, cols)) return cudaErrorInvalidValue;
   const int bytes = static_cast<int>(poa_dp_smem_bytes(threads, ring_rows, cols));
+  if (threads == 512 && poa_cols_per_thread(threads, cols) == 4)
+    return cudaFuncSetAttribute(poa_persistent_kernel<512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (threads == 512) return cudaFuncSetAttribute(poa_persistent_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   return cudaFuncSetAttribute(poa_persistent_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
@@ -655,7 +669,9 @@ cudaError_t poa_persistent_launch(const PoaTask* d_tasks, int n_tasks, int* d_co
   const size_t smem = poa_dp_smem_bytes(threads, ring_rows, cols);
   const int grid = n_tasks < n_sm ? n_tasks : n_sm;
   const SingleTables tabs = make_single_tables(s);
-  if (threads == 512)
+  if (threads == 512 && poa_cols_per_thread(threads, cols) == 4)
+    poa_persistent_kernel<512, 4><<<grid, 512, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, s, tabs, ring_rows);
+  else if (threads == 512)
     poa_persistent_kernel<512, 8><<<grid, 512, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, s, tabs, ring_rows);
   else
     poa_persistent_kernel<256, 16><<<grid, 256, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, s, tabs, ring_rows);

@@ -42,7 +42,7 @@ def _random_group(rng, it, lmax=400):
 
 
 @pytest.mark.parametrize("threads,ring,cols", [(512, 12, 8), (256, 12, 16), (256, 12, 8), (128, 1, 8), (512, 3, 8),
-                                               (128, 24, 8), (256, 2, 16)])
+                                               (128, 24, 8), (256, 2, 16), (512, 24, 4), (512, 5, 4)])
 def test_alignment_pairs_bit_exact(ctx, oracle, threads, ring, cols):
     """Every alignment (node id, read position) list equals the oracle's, for several CTA
     sizes and ring depths (ring 1 forces almost every non-adjacent predecessor through the
