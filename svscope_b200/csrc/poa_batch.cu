@@ -38,6 +38,7 @@ namespace {
 struct PoaJob {
   int64_t group = 0;
   bool done = false;
+  bool force_block = false;      // the next alignment overflowed its slot: give it a full-size block
   double score_per_base = 4.0;   // of the last alignment (drives the pruning guess)
   std::vector<int64_t> seq_ids;
   size_t next = 0;
@@ -53,7 +54,7 @@ struct TaskPlan {
   uint32_t R, L, strip, npass, path_cap, w1, w2;
   uint64_t ldx;
   size_t in_bytes, scratch_bytes, out_bytes, codes_bytes, xrows_bytes, bnd_bytes, band_bytes;
-  bool prune;
+  bool prune, in_slot;
   double cells;
 };
 
@@ -62,7 +63,7 @@ struct WorkerStats {
          h2d = 0, d2h = 0, algo_bytes = 0, exported_rows = 0, rows = 0,
          host_wait_ms = 0, host_merge_ms = 0, host_plan_ms = 0, host_pack_ms = 0,
          refill_ms = 0, starved = 0, launch_ms = 0, final_ms = 0, inflight_ms = 0, h2d_ms = 0, d2h_ms = 0,
-         prune_retries = 0;
+         prune_retries = 0, slot_overflows = 0;
 };
 
 inline double now_ms() {
@@ -308,6 +309,11 @@ class Scheduler {
     // exact pruning pays off on long alignments; scores must stay above -2^21 (kNegBand = -2^22)
     tp->prune = ctx_->prune && tp->L >= 1024 && tp->R >= 1024 &&
                 worst * (static_cast<int64_t>(tp->R) + tp->L + 2) < (1 << 21);
+    // Slot path: pruned alignments store band-limited code rows (the kernel checks the real
+    // size and reports an overflow, which sends the alignment to the block path next round).
+    const size_t small = tp->xrows_bytes + tp->bnd_bytes + tp->band_bytes;
+    const size_t codes_est = tp->prune ? tp->codes_bytes / 2 : tp->codes_bytes;
+    tp->in_slot = persistent_ && !job->force_block && small + codes_est <= slot_bytes_;
     tp->out_bytes = align_up(16 + static_cast<size_t>(tp->path_cap) * 8, 16);
     tp->cells = (static_cast<double>(tp->R) + 1) * (static_cast<double>(tp->L) + 1);
     return true;
@@ -350,7 +356,7 @@ class Scheduler {
     if (chunk.empty()) { st.busy = false; return true; }
     // slot tasks first (largest first), then oversized ones
     std::sort(chunk.begin(), chunk.end(), [&](const TaskPlan& a, const TaskPlan& b) {
-      const bool ba = a.scratch_bytes > slot_bytes_, bb = b.scratch_bytes > slot_bytes_;
+      const bool ba = !a.in_slot, bb = !b.in_slot;
       if (ba != bb) return bb;
       return a.cells > b.cells;
     });
@@ -362,7 +368,7 @@ class Scheduler {
       size_t keep = 0;
       for (; keep < chunk.size(); ++keep) {
         const TaskPlan& t = chunk[keep];
-        const size_t need = t.in_bytes + t.out_bytes + (t.scratch_bytes > slot_bytes_ ? t.scratch_bytes : 0);
+        const size_t need = t.in_bytes + t.out_bytes + (!t.in_slot ? t.scratch_bytes : 0);
         if (keep > 0 && acc + need > budget) break;
         acc += need;
       }
@@ -374,7 +380,7 @@ class Scheduler {
     for (auto& t : chunk) {
       in_total += t.in_bytes;
       out_total += t.out_bytes;
-      if (t.scratch_bytes > slot_bytes_) big_total += t.scratch_bytes; else ++st.n_slot;
+      if (!t.in_slot) big_total += t.scratch_bytes; else ++st.n_slot;
     }
     st.n_big = n - st.n_slot;
     in_total = align_up(in_total, 256);
@@ -422,7 +428,7 @@ class Scheduler {
       in_off += chunk[k].in_bytes;
       st.out_offs[k] = out_off;
       out_off += chunk[k].out_bytes;
-      if (chunk[k].scratch_bytes > slot_bytes_) { big_offs[k] = big_off; big_off += chunk[k].scratch_bytes; }
+      if (!chunk[k].in_slot) { big_offs[k] = big_off; big_off += chunk[k].scratch_bytes; }
     }
     parallel_for(n, threads_, [&](int k) {
       const TaskPlan& tp = chunk[k];
@@ -451,16 +457,18 @@ class Scheduler {
       t.w1 = tp.w1;
       t.w2 = tp.w2;
       t.ldx = tp.ldx;
-      t.off_codes = 0;
-      t.off_xrows = tp.codes_bytes;
-      t.off_bnd = tp.codes_bytes + tp.xrows_bytes;
-      t.off_band = tp.codes_bytes + tp.xrows_bytes + tp.bnd_bytes;
-      t.prune = (tp.prune && tp.scratch_bytes <= slot_bytes_) ? 1u : 0u;   // persistent path only
+      // slot layout: [exported rows | strip boundaries | bands | traceback codes (rest of the slot)]
+      t.off_xrows = 0;
+      t.off_bnd = tp.xrows_bytes;
+      t.off_band = tp.xrows_bytes + tp.bnd_bytes;
+      t.off_codes = tp.xrows_bytes + tp.bnd_bytes + tp.band_bytes;
+      t.codes_cap = tp.in_slot ? slot_bytes_ - t.off_codes : tp.codes_bytes;
+      t.prune = (tp.prune && tp.in_slot) ? 1u : 0u;   // persistent path only
       // guess: score per read base of the previous alignment of this graph, minus a margin
       t.lb_guess = static_cast<int32_t>((tp.job->score_per_base - prune_margin_) * static_cast<double>(tp.L)) - 40;
-      if (tp.scratch_bytes > slot_bytes_) {
+      if (!tp.in_slot) {
         uint8_t* base = d_big + big_offs[k];
-        t.codes = base;
+        t.codes = base + t.off_codes;
         t.xrows = reinterpret_cast<int32_t*>(base + t.off_xrows);
         t.bnd = reinterpret_cast<int32_t*>(base + t.off_bnd);
       } else {
@@ -521,11 +529,17 @@ class Scheduler {
     stats.alignments += n;
     std::vector<double> path_pairs(n, 0.0);
     std::vector<int32_t> retries(n, 0);
+    std::vector<uint8_t> overflowed(n, 0);
     parallel_for(n, threads_, [&](int k) {
       const TaskPlan& tp = st.inflight[k];
       const int32_t* res = reinterpret_cast<const int32_t*>(st.h_out + st.out_offs[k]);
       const int32_t* path = res + 4;
       const int32_t np = res[2];
+      if (res[0] == -2) {   // band-limited codes did not fit the slot: repeat with a full-size block
+        tp.job->force_block = true;
+        overflowed[k] = 1;
+        return;
+      }
       if (np < 0 || static_cast<uint32_t>(np) > tp.path_cap || res[0] <= 0) {
         set_err(SVS_ERR_INTERNAL, "traceback failed (best_row=" + std::to_string(res[0]) + ", n=" + std::to_string(np) + ")");
         return;
@@ -548,12 +562,14 @@ class Scheduler {
         job->graph.add_alignment(nodes.data(), pos.data(), static_cast<size_t>(np),
                                  reads_->host.data() + reads_->off[tp.seq_id], tp.L);
         ++job->next;
+        job->force_block = false;
       } catch (const std::exception& ex) {
         set_err(SVS_ERR_INTERNAL, std::string("add_alignment: ") + ex.what());
       }
     });
     for (double v : path_pairs) stats.algo_bytes += 8.0 * v;
     for (int32_t v : retries) stats.prune_retries += v;
+    for (uint8_t v : overflowed) { stats.slot_overflows += v; stats.alignments -= v; }
     blocks_.release(st.blk_off, st.blk_bytes);
     st.blk_bytes = 0;
     st.inflight.clear();

@@ -247,7 +247,11 @@ SVS_HD int32_t cell_bound(const Scores& s, int32_t dmin, int32_t dmax, int32_t s
 // Everything the traceback needs to read.
 struct TbView {
   const uint8_t* codes;
-  uint32_t w1, w2;
+  uint32_t w1, w2;            // row pitch in bytes: single-predecessor rows / others
+  // band-limited code rows (pruned alignments): row r holds the cells from column
+  // 1 + first_chunk(r)*cols on, first_chunk(r) = (band[2r]-1)/cols; nullptr = full-width rows
+  const int32_t* band;
+  uint32_t cols;
   const uint32_t* single_before;
   const uint16_t* col0code;
   const uint32_t* pred_off;
@@ -260,8 +264,10 @@ SVS_HD uint32_t tb_code_at(const TbView& v, const Scores& s, uint32_t ii, uint32
   if (jj == 0) return v.col0code[ii];
   const uint64_t n1 = v.single_before[ii];
   const uint8_t* row = v.codes + n1 * v.w1 + (static_cast<uint64_t>(ii - 1) - n1) * v.w2;
-  if (v.pred_off[ii + 1] - v.pred_off[ii] == 1) return row[jj - 1];   // 1-byte code: in-edge indices are 0
-  return reinterpret_cast<const uint16_t*>(row)[jj - 1];
+  uint32_t col = jj - 1;
+  if (v.band != nullptr) col -= (static_cast<uint32_t>(v.band[2 * ii] - 1) / v.cols) * v.cols;
+  if (v.pred_off[ii + 1] - v.pred_off[ii] == 1) return row[col];   // 1-byte code: in-edge indices are 0
+  return reinterpret_cast<const uint16_t*>(row)[col];
 }
 
 // One iteration of the traceback loop at (i, j) != (0, 0), including the gap-extension walks
@@ -314,7 +320,7 @@ SVS_HD int32_t traceback_walk(uint32_t best_row, uint32_t L, const uint8_t* code
                               const uint32_t* single_before, const uint16_t* col0code, const uint32_t* pred_off,
                               const uint32_t* preds, const uint32_t* node_id, const Scores& s,
                               int32_t* out_pairs, int32_t cap) {
-  const TbView v{codes, w1, w2, single_before, col0code, pred_off, preds, node_id};
+  const TbView v{codes, w1, w2, nullptr, 8, single_before, col0code, pred_off, preds, node_id};
   uint32_t i = best_row, j = L;
   int32_t n = 0;
   while (!(i == 0 && j == 0)) {

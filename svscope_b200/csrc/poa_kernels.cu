@@ -51,6 +51,7 @@ struct Stage {
   uint32_t single_before[kRowBatch];
   int16_t tlo[kRowBatch], thi[kRowBatch];   // active thread range of the row in this strip (empty: tlo > thi)
   int16_t ptlo[kPredCap], pthi[kPredCap];   // the same for every staged predecessor row
+  int32_t cbase[kRowBatch];                 // first stored column - 1 of the row's code row (band-limited rows)
   int wlo, whi;                             // warps that own a band cell of some row of the batch (empty: wlo > whi)
   int32_t bA[kRowBatch], bE[kRowBatch], bQ[kRowBatch];
   uint8_t letter[kRowBatch];
@@ -86,6 +87,9 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
                                          const int ring_rows, unsigned char* smem_raw, const int32_t* band) {
   static_assert(kC == 4 || kC == 8 || kC == 16, "columns per thread");
   const int32_t NEGW = pack_cell(kNegBand, kNeg, kNeg);
+  // code row pitches: full-width rows, or (pruned) the widest band of the alignment (band[0..1])
+  const uint64_t pitch1 = band != nullptr ? static_cast<uint32_t>(__ldcg(band)) : tk.w1;
+  const uint64_t pitch2 = band != nullptr ? static_cast<uint32_t>(__ldcg(band + 1)) : tk.w2;
   constexpr int NW = T / 32;
   constexpr int WC = T * kC;
   int32_t* ring = reinterpret_cast<int32_t*>(smem_raw);
@@ -134,6 +138,7 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
         st.single_before[tid] = tk.single_before[i];
         int32_t blo, bhi;
         row_band<MODE>(tk, band, i, blo, bhi);
+        st.cbase[tid] = (band != nullptr && blo >= 1) ? ((blo - 1) / kC) * kC : 0;
         strip_threads<kC>(blo, bhi, static_cast<int32_t>(jb), static_cast<int32_t>(je), st.tlo[tid], st.thi[tid]);
         // the row's own left boundary: column 0 (exact) in the first strip, else the last
         // chunk of the previous strip if the band covered it
@@ -389,22 +394,23 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
           }
           if (MODE == kFull) {
             const uint64_t n1 = st.single_before[r];
-            uint8_t* crow = tk.codes + n1 * tk.w1 + (static_cast<uint64_t>(i - 1) - n1) * tk.w2;
+            uint8_t* crow = tk.codes + n1 * pitch1 + (static_cast<uint64_t>(i - 1) - n1) * pitch2;
+            const uint64_t ccol = static_cast<uint64_t>(j0 - 1) - static_cast<uint32_t>(st.cbase[r]);
             if (single) {  // single predecessor: low bytes only
               uint32_t b[kC / 4];
 #pragma unroll
               for (int q = 0; q < kC / 4; ++q)
                 b[q] = (cw[2 * q] & 0xffu) | ((cw[2 * q] >> 8) & 0xff00u) | ((cw[2 * q + 1] & 0xffu) << 16) |
                        ((cw[2 * q + 1] & 0xff0000u) << 8);
-              if (kC == 4) *reinterpret_cast<uint32_t*>(crow + (j0 - 1)) = b[0];
-              else if (kC == 8) *reinterpret_cast<uint2*>(crow + (j0 - 1)) = make_uint2(b[0], b[kC / 4 - 1]);
-              else *reinterpret_cast<uint4*>(crow + (j0 - 1)) = make_uint4(b[0], b[1], b[kC / 4 - 2], b[kC / 4 - 1]);
+              if (kC == 4) *reinterpret_cast<uint32_t*>(crow + ccol) = b[0];
+              else if (kC == 8) *reinterpret_cast<uint2*>(crow + ccol) = make_uint2(b[0], b[kC / 4 - 1]);
+              else *reinterpret_cast<uint4*>(crow + ccol) = make_uint4(b[0], b[1], b[kC / 4 - 2], b[kC / 4 - 1]);
             } else if (kC == 4) {
-              *reinterpret_cast<uint2*>(crow + 2 * static_cast<uint64_t>(j0 - 1)) = make_uint2(cw[0], cw[1]);
+              *reinterpret_cast<uint2*>(crow + 2 * ccol) = make_uint2(cw[0], cw[1]);
             } else {
 #pragma unroll
               for (int q = 0; q < kC / 8; ++q)
-                *reinterpret_cast<uint4*>(crow + 2 * static_cast<uint64_t>(j0 - 1) + 16 * q) =
+                *reinterpret_cast<uint4*>(crow + 2 * ccol + 16 * q) =
                     make_uint4(cw[4 * q], cw[4 * q + 1], cw[4 * q + 2], cw[4 * q + 3]);
             }
           }
@@ -451,9 +457,13 @@ __global__ void __launch_bounds__(T, (kC == 16 ? 1 : 512 / T)) poa_dp_kernel(con
 
 // Band of every row: the columns whose upper bound (cell_bound, concave in the column) reaches
 // the lower bound `lb` of the optimal score.
-template <int T>
+template <int T, int kC>
 __device__ void compute_bands(const PoaTask& tk, const Scores& s, int32_t lb, bool have_lb, int32_t* band) {
   const int32_t L = static_cast<int32_t>(tk.L);
+  __shared__ int s_widest;
+  if (threadIdx.x == 0) s_widest = kC;
+  __syncthreads();
+  int widest = kC;
   for (uint32_t i = 1 + threadIdx.x; i <= tk.R; i += T) {
     int32_t lo = 1, hi = L;
     if (have_lb) {
@@ -481,15 +491,26 @@ __device__ void compute_bands(const PoaTask& tk, const Scores& s, int32_t lb, bo
     }
     band[2 * i] = lo;
     band[2 * i + 1] = hi;
+    if (lo <= hi) widest = max(widest, ((hi - 1) / kC - (lo - 1) / kC + 1) * kC);   // stored cells of the row
   }
+  atomicMax(&s_widest, widest);
+  __syncthreads();
+  if (threadIdx.x == 0) {   // row 0 has no codes: its two entries carry the row pitches (bytes)
+    const int32_t p1 = (s_widest + 15) / 16 * 16;
+    band[0] = p1;
+    band[1] = 2 * p1;
+  }
+  __syncthreads();
 }
 
 // Traceback by one warp.  Long diagonal runs through chain rows (one predecessor = the
 // previous row) are the common case: the 32 lanes look at the cells (i-k, j-k) in parallel
 // and the walk advances by the number of leading lanes whose cell is such a diagonal move;
 // everything else is one serial step of the reference walk (tb_step) by lane 0.
-__device__ void tb_walk_warp(const PoaTask& tk, const Scores& s) {
-  const TbView v{tk.codes, tk.w1, tk.w2, tk.single_before, tk.col0code, tk.pred_off, tk.preds, tk.node_id};
+__device__ void tb_walk_warp(const PoaTask& tk, const Scores& s, const int32_t* band, int cols) {
+  const uint32_t p1 = band != nullptr ? static_cast<uint32_t>(band[0]) : tk.w1;
+  const uint32_t p2 = band != nullptr ? static_cast<uint32_t>(band[1]) : tk.w2;
+  const TbView v{tk.codes, p1, p2, band, static_cast<uint32_t>(cols), tk.single_before, tk.col0code, tk.pred_off, tk.preds, tk.node_id};
   const int lane = threadIdx.x & 31;
   uint32_t i = static_cast<uint32_t>(tk.result[0]), j = tk.L;
   int32_t n = 0;
@@ -500,9 +521,17 @@ __device__ void tb_walk_warp(const PoaTask& tk, const Scores& s) {
     int32_t node = 0;
     if (i > static_cast<uint32_t>(lane) && j > static_cast<uint32_t>(lane)) {
       const uint32_t r = i - lane, c = j - lane;
-      if (tk.flags[r] & kFlagChain) {
+      bool inside = true;
+      uint32_t col = c - 1;
+      if (band != nullptr) {   // a speculated cell may lie outside the stored band of its row
+        const int32_t blo = band[2 * r], bhi = band[2 * r + 1];
+        const uint32_t first = blo >= 1 ? (static_cast<uint32_t>(blo - 1) / cols) * cols : 0u;
+        inside = blo <= bhi && c - 1 >= first && static_cast<int32_t>(c) <= bhi;
+        col -= first;
+      }
+      if (inside && (tk.flags[r] & kFlagChain)) {
         const uint64_t n1 = tk.single_before[r];
-        const uint32_t cd = tk.codes[n1 * tk.w1 + (static_cast<uint64_t>(r - 1) - n1) * tk.w2 + (c - 1)];
+        const uint32_t cd = tk.codes[n1 * p1 + (static_cast<uint64_t>(r - 1) - n1) * p2 + col];
         if ((cd & 3u) == kMoveDiag) {
           mine = true;
           node = static_cast<int32_t>(tk.node_id[r]);
@@ -566,10 +595,15 @@ __global__ void __launch_bounds__(T, 1) poa_persistent_kernel(const PoaTask* __r
       band = reinterpret_cast<int32_t*>(slot + tk.off_band);
       int32_t lb = tk.lb_guess;
       bool have_lb = true;
+      bool overflow = false;
       for (int attempt = 0; attempt < 3; ++attempt) {
         if (threadIdx.x == 0) { tk.result[0] = 0; tk.result[1] = INT32_MIN; }
-        compute_bands<T>(tk, s, lb, have_lb, band);
-        __syncthreads();
+        compute_bands<T, kC>(tk, s, lb, have_lb, band);
+        {   // do the band-limited code rows fit the slot?
+          const uint64_t n1 = tk.single_before[tk.R + 1];
+          const uint64_t need = n1 * static_cast<uint32_t>(band[0]) + (static_cast<uint64_t>(tk.R) - n1) * static_cast<uint32_t>(band[1]) + 64;
+          if (need > tk.codes_cap) { overflow = true; break; }
+        }
         dp_align<T, kC, kFull>(tk, s, tabs, ring_rows, smem_raw, band);
         const int32_t found_row = tk.result[0], found = tk.result[1];
         if (!have_lb || (found_row > 0 && found >= lb)) break;   // consistent with the bound used
@@ -578,10 +612,14 @@ __global__ void __launch_bounds__(T, 1) poa_persistent_kernel(const PoaTask* __r
         lb = found;
         __syncthreads();
       }
+      if (overflow) {   // the host repeats this alignment with an explicit full-size block
+        if (threadIdx.x == 0) { tk.result[0] = -2; tk.result[2] = 0; }
+        continue;
+      }
     } else {
       dp_align<T, kC, kFull>(tk, s, tabs, ring_rows, smem_raw, nullptr);
     }
-    if (threadIdx.x < 32) tb_walk_warp(tk, s);
+    if (threadIdx.x < 32) tb_walk_warp(tk, s, band, kC);
   }
 }
 

@@ -40,6 +40,7 @@ struct PoaTask {
   uint64_t off_codes, off_xrows, off_bnd, off_band;
   uint32_t prune;             // 1: prune with bands from `lb_guess` (retry inside the kernel if it was too high)
   int32_t lb_guess;           // guessed lower bound of the optimal score
+  uint64_t codes_cap;         // bytes available for traceback codes (pruned alignments use band-limited rows)
 };
 
 }  // namespace svs
