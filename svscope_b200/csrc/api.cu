@@ -51,6 +51,10 @@ int ensure_arena(svs_ctx* ctx) {
   if (want > free_b) return fail(ctx, SVS_ERR_CAPACITY, "arena_mb exceeds free device memory");
   SVS_CUDA(ctx, cudaMalloc(&ctx->arena, want));
   ctx->arena_bytes = want;
+  if (!ctx->slot_flags) {
+    SVS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->slot_flags), 4096 * sizeof(int)));
+    SVS_CUDA(ctx, cudaMemset(ctx->slot_flags, 0, 4096 * sizeof(int)));
+  }
   return SVS_OK;
 }
 
@@ -95,6 +99,7 @@ void svs_destroy(svs_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->arena) cudaFree(ctx->arena);
+  if (ctx->slot_flags) cudaFree(ctx->slot_flags);
   delete ctx;
 }
 

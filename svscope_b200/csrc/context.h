@@ -14,7 +14,7 @@ struct svs_ctx {
   int device = 0;
   std::string error;
   // options
-  int poa_threads = 512;
+  int poa_threads = 256;   // 256 threads x 8 columns: two resident alignments per SM
   int prune = 1;       // exact score-bound pruning of DP cells (persistent kernel)
   int poa_cols = 8;    // read columns per thread (16 only with 256 threads)
   int ring_rows = 12;
@@ -24,6 +24,7 @@ struct svs_ctx {
   int inflight = 0;    // (unused by the round scheduler)
   int streams = 0;     // concurrent round streams (0 = 2)
   // device arena shared by the batched calls (allocated lazily, reused)
+  int* slot_flags = nullptr;   // busy flags of the per-SM scratch slots (two resident CTAs per SM)
   void* arena = nullptr;
   size_t arena_bytes = 0;
   int sm_count = 0;

@@ -182,7 +182,8 @@ class Scheduler {
     // otherwise every alignment takes the classic path with explicit arena blocks
     persistent_ = poa_persistent_supported(ctx_->poa_threads, ctx_->ring_rows, ctx_->poa_cols);
     cols_ = static_cast<uint32_t>(poa_cols_per_thread(ctx_->poa_threads, ctx_->poa_cols));
-    n_slots_ = std::max(n_sm_, ctx_->n_smid);
+    ctas_per_sm_ = std::max(1, poa_persistent_ctas_per_sm(ctx_->poa_threads, ctx_->ring_rows, ctx_->poa_cols));
+    n_slots_ = std::max(n_sm_, ctx_->n_smid) * ctas_per_sm_;
     slot_bytes_ = persistent_ ? (static_cast<size_t>(static_cast<double>(ctx_->arena_bytes) * 0.88) / n_slots_) / 4096 * 4096 : 0;
     slot_base_ = static_cast<uint8_t*>(ctx_->arena);
     block_base_ = slot_base_ + slot_bytes_ * n_slots_;
@@ -496,7 +497,7 @@ class Scheduler {
               check(cudaMemsetAsync(st.d_counter, 0, sizeof(int), cs), "counter") &&
               check(cudaEventRecord(st.ev[0], cs), "event");
     if (ok && st.n_slot > 0)
-      ok = check(poa_persistent_launch(d_tasks, st.n_slot, st.d_counter, slot_base_, slot_bytes_, n_sm_, s_,
+      ok = check(poa_persistent_launch(d_tasks, st.n_slot, st.d_counter, slot_base_, slot_bytes_, ctx_->slot_flags, n_sm_, s_,
                                        ctx_->poa_threads, ctx_->ring_rows, ctx_->poa_cols, cs), "poa_persistent_kernel");
     if (ok && st.n_big > 0)
       ok = check(poa_dp_launch(d_tasks + st.n_slot, st.n_big, s_, ctx_->poa_threads, ctx_->ring_rows, ctx_->poa_cols, cs), "poa_dp_kernel");
@@ -582,7 +583,7 @@ class Scheduler {
   Scores s_;
   svs_poa_result* res_;
   bool want_msa_;
-  int threads_ = 1, n_sm_ = 1, n_slots_ = 1;
+  int threads_ = 1, n_sm_ = 1, n_slots_ = 1, ctas_per_sm_ = 1;
   uint32_t cols_ = 8;
   bool persistent_ = false;
   double prune_margin_ = 0.10;   // score per base subtracted from the previous alignment's rate

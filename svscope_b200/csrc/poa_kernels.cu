@@ -566,15 +566,26 @@ __device__ void tb_walk_warp(const PoaTask& tk, const Scores& s, const int32_t* 
 // of its SM (slot = %smid: with > 114 KB of shared memory only one such CTA fits an SM), and
 // walks the traceback itself as soon as the dynamic programme of the alignment is done.
 template <int T, int kC>
-__global__ void __launch_bounds__(T, 1) poa_persistent_kernel(const PoaTask* __restrict__ tasks, const int n_tasks,
-                                                                    int* __restrict__ counter, uint8_t* slot_base,
-                                                                    const uint64_t slot_bytes, const Scores s,
-                                                                    const SingleTables tabs, const int ring_rows) {
+__global__ void __launch_bounds__(T, (T == 256 && kC == 8) ? 2 : 1)
+poa_persistent_kernel(const PoaTask* __restrict__ tasks, const int n_tasks, int* __restrict__ counter, uint8_t* slot_base,
+                      const uint64_t slot_bytes, int* __restrict__ slot_flags, const int slots_per_sm, const Scores s,
+                      const SingleTables tabs, const int ring_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_next;
+  __shared__ int s_slot;
   unsigned smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-  uint8_t* slot = slot_base + static_cast<uint64_t>(smid) * slot_bytes;
+  // scratch slot: one per SM, or (two resident CTAs per SM) one of the SM's slots taken with a flag
+  if (threadIdx.x == 0) {
+    int k = 0;
+    if (slots_per_sm > 1) {
+      while (atomicCAS(&slot_flags[smid * slots_per_sm + k], 0, 1) != 0) k = (k + 1 == slots_per_sm) ? 0 : k + 1;
+    }
+    s_slot = static_cast<int>(smid) * slots_per_sm + k;
+  }
+  __syncthreads();
+  const int my_slot = s_slot;
+  uint8_t* slot = slot_base + static_cast<uint64_t>(my_slot) * slot_bytes;
   while (true) {
     __syncthreads();
     if (threadIdx.x == 0) s_next = atomicAdd(counter, 1);
@@ -620,6 +631,11 @@ __global__ void __launch_bounds__(T, 1) poa_persistent_kernel(const PoaTask* __r
       dp_align<T, kC, kFull>(tk, s, tabs, ring_rows, smem_raw, nullptr);
     }
     if (threadIdx.x < 32) tb_walk_warp(tk, s, band, kC);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && slots_per_sm > 1) {
+    __threadfence();
+    atomicExch(&slot_flags[my_slot], 0);
   }
 }
 
@@ -685,34 +701,49 @@ cudaError_t poa_dp_launch(const PoaTask* d_tasks, int n_tasks, const Scores& s, 
   return cudaGetLastError();
 }
 
-// persistent mode needs exactly one resident CTA per SM: > 114 KB of shared memory
+// Persistent mode needs a fixed number of resident CTAs per SM, enforced by shared memory:
+// one (> 114 KB per CTA) for 512x8, 512x4, 256x16; two (76..113 KB per CTA) for 256x8.
+// Returns that number, 0 if the configuration cannot run persistently.
+int poa_persistent_ctas_per_sm(int threads, int ring_rows, int cols) {
+  const size_t smem = poa_dp_smem_bytes(threads, ring_rows, cols);
+  const int c = poa_cols_per_thread(threads, cols);
+  if ((threads == 512 || (threads == 256 && c == 16)) && smem > 114 * 1024) return 1;
+  if (threads == 256 && c == 8 && smem > 76 * 1024 && smem <= 113 * 1024) return 2;
+  return 0;
+}
+
 bool poa_persistent_supported(int threads, int ring_rows, int cols) {
-  const bool shape = threads == 512 || (threads == 256 && poa_cols_per_thread(threads, cols) == 16);
-  return shape && poa_dp_smem_bytes(threads, ring_rows, cols) > 114 * 1024;
+  return poa_persistent_ctas_per_sm(threads, ring_rows, cols) > 0;
 }
 
 cudaError_t poa_persistent_configure(int threads, int ring_rows, int cols) {
   if (!poa_persistent_supported(threads, ring_rows, cols)) return cudaErrorInvalidValue;
   const int bytes = static_cast<int>(poa_dp_smem_bytes(threads, ring_rows, cols));
-  if (threads == 512 && poa_cols_per_thread(threads, cols) == 4)
+  const int c = poa_cols_per_thread(threads, cols);
+  if (threads == 512 && c == 4)
     return cudaFuncSetAttribute(poa_persistent_kernel<512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (threads == 512) return cudaFuncSetAttribute(poa_persistent_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  return cudaFuncSetAttribute(poa_persistent_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (c == 16) return cudaFuncSetAttribute(poa_persistent_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return cudaFuncSetAttribute(poa_persistent_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 cudaError_t poa_persistent_launch(const PoaTask* d_tasks, int n_tasks, int* d_counter, uint8_t* slot_base,
-                                  uint64_t slot_bytes, int n_sm, const Scores& s, int threads, int ring_rows, int cols,
-                                  cudaStream_t stream) {
+                                  uint64_t slot_bytes, int* slot_flags, int n_sm, const Scores& s, int threads,
+                                  int ring_rows, int cols, cudaStream_t stream) {
   if (n_tasks <= 0) return cudaSuccess;
   const size_t smem = poa_dp_smem_bytes(threads, ring_rows, cols);
-  const int grid = n_tasks < n_sm ? n_tasks : n_sm;
+  const int spm = poa_persistent_ctas_per_sm(threads, ring_rows, cols);
+  const int grid = n_tasks < n_sm * spm ? n_tasks : n_sm * spm;
   const SingleTables tabs = make_single_tables(s);
-  if (threads == 512 && poa_cols_per_thread(threads, cols) == 4)
-    poa_persistent_kernel<512, 4><<<grid, 512, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, s, tabs, ring_rows);
+  const int c = poa_cols_per_thread(threads, cols);
+  if (threads == 512 && c == 4)
+    poa_persistent_kernel<512, 4><<<grid, 512, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, slot_flags, spm, s, tabs, ring_rows);
   else if (threads == 512)
-    poa_persistent_kernel<512, 8><<<grid, 512, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, s, tabs, ring_rows);
+    poa_persistent_kernel<512, 8><<<grid, 512, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, slot_flags, spm, s, tabs, ring_rows);
+  else if (c == 16)
+    poa_persistent_kernel<256, 16><<<grid, 256, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, slot_flags, spm, s, tabs, ring_rows);
   else
-    poa_persistent_kernel<256, 16><<<grid, 256, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, s, tabs, ring_rows);
+    poa_persistent_kernel<256, 8><<<grid, 256, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, slot_flags, spm, s, tabs, ring_rows);
   return cudaGetLastError();
 }
 

@@ -46,8 +46,9 @@ def _random_group(rng, it, lmax=400):
 def test_alignment_pairs_bit_exact(ctx, oracle, threads, ring, cols):
     """Every alignment (node id, read position) list equals the oracle's, for several CTA
     sizes and ring depths (ring 1 forces almost every non-adjacent predecessor through the
-    exported rows in global memory).  (512, 12, 8) and (256, 12, 16) are the persistent
-    configurations (per-SM scratch slots, fused traceback); the others take the classic launch path."""
+    exported rows in global memory).  (256, 12, 8) [default: two resident CTAs per SM], (512, 12, 8), (512, 24, 4) and
+    (256, 12, 16) run the persistent kernel (scratch slots, fused traceback); the others take the
+    classic launch path."""
     from svscope_b200.poa_api import align_pairs
     ctx.set_option("poa_threads", threads)
     ctx.set_option("ring_rows", ring)
@@ -63,7 +64,7 @@ def test_alignment_pairs_bit_exact(ctx, oracle, threads, ring, cols):
                 assert a.shape == b.shape and np.array_equal(a, b)
             o.close()
     finally:
-        ctx.set_option("poa_threads", 512)
+        ctx.set_option("poa_threads", 256)
         ctx.set_option("ring_rows", 12)
         ctx.set_option("poa_cols", 8)
 

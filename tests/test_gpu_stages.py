@@ -199,3 +199,25 @@ def test_raw_bed_roundtrip(ctx, oracle, tmp_path):
     args.Continue = True
     SVscope.localGraph_npz(args)
     assert len(open(path).read().splitlines()) == 4
+
+
+@pytest.mark.parametrize("name", ["large_c1", "large_c3_scaled"])
+def test_full_size_windows_equal_oracle_golden(ctx, golden_dir, name):
+    """BASELINE.json configs[0] at full size (30+30 reads ~10 kb, 2 kb somatic DEL) and a scaled
+    configs[2] (tandem-repeat INS, 10 % error): record, MSA and consensus equal the oracle's
+    (tests/golden/large_*.json, made by oracle/gen_golden_large.py; minutes of CPU there)."""
+    import hashlib
+    import json
+    from svscope_b200.DecisionMaker import Decision
+    from svscope_b200.spoa import poa
+    g = json.load(open(os.path.join(golden_dir, name + ".json")))
+    w = synth.make_c1(seed=1) if name == "large_c1" else \
+        synth.make_c3(seed=3, total_len=6000, n_tumor=20, n_normal=20, n_carriers=10, err=0.10)
+    cons, msa = poa(w[0], 1)
+    assert len(msa[0]) == g["msa_cols"]
+    assert hashlib.sha256("\n".join(msa).encode()).hexdigest() == g["msa_sha"]
+    assert hashlib.sha256(cons.encode()).hexdigest() == g["consensus_sha"]
+    assert [r.replace("-", "") for r in msa] == w[0]
+    np.random.seed(2023)
+    rec = Decision(w[4], w[0], w[1], w[2], w[3])
+    assert [str(x) for x in rec] == g["record"]
