@@ -48,25 +48,29 @@ def read_tag(read_id: str) -> str:
     return read_id.split("|")[0].split("_")[-1]
 
 
-def encode_msa(msa: Sequence[str]) -> np.ndarray:
-    """SeqEncoder over all rows (DataScanner.py:124-129, 214); KeyError on foreign symbols."""
+def encode_msa(msa) -> np.ndarray:
+    """SeqEncoder over all rows (DataScanner.py:124-129, 214); KeyError on foreign symbols.
+    ``msa`` is a list of row strings or a (rows, cols) uint8 array of characters."""
     if len(msa) == 0:
         return np.zeros((0, 0), np.int64)
-    raw = np.frombuffer("".join(msa).encode(), np.uint8).reshape(len(msa), -1)
+    if isinstance(msa, np.ndarray):
+        raw = msa
+    else:
+        raw = np.frombuffer("".join(msa).encode(), np.uint8).reshape(len(msa), -1)
     enc = ENC_LUT[raw]
     if (enc == 255).any():
         raise KeyError(chr(int(raw[enc == 255][0])))
     return enc
 
 
-def margin_columns(ref_row: str, flank_5: str, flank_3: str) -> np.ndarray:
+def margin_columns(ref_row, flank_5: str, flank_3: str) -> np.ndarray:
     """CallMargin (DataScanner.py:146-165) without the per-character Python loop.
 
     Forward walk: the collected non-gap prefix can equal flank_5 only when it has len(flank_5)
     characters, so either the first len(flank_5) non-gap columns are returned (prefix matches)
     or the walk never stops and returns all of them.  The backward walk covers columns
     len-1 .. 1 only (column 0 is never visited, DataScanner.py:159)."""
-    row = np.frombuffer(ref_row.encode(), np.uint8)
+    row = ref_row if isinstance(ref_row, np.ndarray) else np.frombuffer(ref_row.encode(), np.uint8)
     nongap = np.flatnonzero(row != ord("-"))
     n5, n3 = len(flank_5), len(flank_3)
     if n5 == 0:
@@ -105,7 +109,8 @@ def msa_features(ctx: Context, encs: List[np.ndarray], drops: List[np.ndarray], 
     enc_cat = np.zeros(max(int(enc_off[-1]), 1), np.int8)
     drop_cat = np.zeros(max(int(col_off[-1]), 1), np.uint8)
     for w in range(nw):
-        enc_cat[enc_off[w]:enc_off[w + 1]] = encs[w].astype(np.int8).ravel()
+        e = encs[w]
+        enc_cat[enc_off[w]:enc_off[w + 1]] = (e.view(np.int8) if e.dtype == np.uint8 else e.astype(np.int8)).reshape(-1)
         drop_cat[col_off[w]:col_off[w + 1]] = drops[w]
     keep = np.zeros_like(drop_cat)
     nf = np.zeros(nw, np.int32)
@@ -351,7 +356,7 @@ def localgraph_batch(windows, ctx: Optional[Context] = None, reads: Optional[Rea
     # ---- stage 2: window MSA ---------------------------------------------------------------
     t1 = time.perf_counter()
     groups = [list(range(int(base[i]), int(base[i + 1]))) for i in live]
-    _, msas, st_msa = poa_groups(ctx, reads, groups, want_msa=True)
+    _, msas, st_msa = poa_groups(ctx, reads, groups, want_msa=True, as_array=True)
     tm["poa_msa"] = time.perf_counter() - t1
     # ---- stage 3: encode, margins, features ---------------------------------------------------
     t1 = time.perf_counter()

@@ -34,8 +34,8 @@ constexpr int kMaxW = 32;
 
 __device__ __forceinline__ int sym_of(uint8_t ch) { return (ch >> 1) & 3; }  // A,C,T,G -> 0,1,2,3
 
-// One strip of at most 1024*W pattern rows starting at row `row0`.  Returns (in the lane that
-// owns the last pattern row of the strip) the sum of horizontal deltas at that row.
+// One strip of at most 1024*W pattern rows starting at row `row0`.  Returns this lane's share of
+// D[row0+rows][n] - D[row0][n] (sum of the vertical deltas of its rows in the last column).
 template <int W>
 __device__ int strip_pass(const PairTask& t, int row0, int rows, bool first_strip, bool last_strip, int lane) {
   // pattern as two bit planes of the 2-bit symbol (half the registers of four match masks);
@@ -56,10 +56,6 @@ __device__ int strip_pass(const PairTask& t, int row0, int rows, bool first_stri
       }
     }
   }
-  const int last = rows - 1;
-  const int last_lane = last / (32 * W), last_word = (last / 32) % W;
-  const uint32_t last_bit = 1u << (last % 32);
-  int score = 0;
   int carry = 0;  // packed: (hout + 1) | sym << 2 | valid << 4 handed to the next lane
   const int n = t.lb;
   for (int step = 0; step < n + 31; ++step) {
@@ -86,7 +82,6 @@ __device__ int strip_pass(const PairTask& t, int row0, int rows, bool first_stri
         const uint32_t xh = (((eq & Pv) + Pv) ^ Pv) | eq;
         uint32_t ph = Mv | ~(xh | Pv);
         uint32_t mh = Pv & xh;
-        if (lane == last_lane && w == last_word) score += ((ph & last_bit) ? 1 : 0) - ((mh & last_bit) ? 1 : 0);
         const int ho = static_cast<int>(ph >> 31) - static_cast<int>(mh >> 31);
         ph <<= 1; mh <<= 1;
         if (hout < 0) mh |= 1u; else if (hout > 0) ph |= 1u;
@@ -98,22 +93,28 @@ __device__ int strip_pass(const PairTask& t, int row0, int rows, bool first_stri
     }
     carry = (hout + 1) | (sym << 2) | (valid << 4);
   }
-  return score;
+  // After the last text character Pv / Mv hold the vertical deltas D[i][n] - D[i-1][n] of the
+  // strip's rows, so the strip adds popcount(Pv) - popcount(Mv) over its valid rows to D[.][n].
+  int delta = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const int base = (lane * W + w) * 32;
+    const int nvalid = rows - base;
+    const uint32_t mask = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+    delta += __popc(pv[w] & mask) - __popc(mv[w] & mask);
+  }
+  return delta;
 }
 
 template <int W>
 __device__ int pair_distance(const PairTask& t, int lane) {
   const int cap = 32 * 32 * W;
-  int total = t.la;
+  int total = t.lb;   // D[0][n] = n
   for (int row0 = 0; row0 < t.la; row0 += cap) {
     const int rows = min(cap, t.la - row0);
     const bool last_strip = row0 + cap >= t.la;
-    const int sc = strip_pass<W>(t, row0, rows, row0 == 0, last_strip, lane);
-    // only the last strip's bottom row is the distance row
-    const int last = rows - 1;
-    const int owner = last / (32 * W);
-    const int v = __shfl_sync(0xffffffffu, sc, owner);
-    if (last_strip) total += v;
+    const int part = strip_pass<W>(t, row0, rows, row0 == 0, last_strip, lane);
+    total += __reduce_add_sync(0xffffffffu, part);
     __syncwarp();
   }
   return total;

@@ -17,10 +17,12 @@ DEFAULT_SCORES = dict(m=5, n=-4, g=-8, e=-6, q=-10, c=-4)
 
 
 def poa_groups(ctx: Context, reads: ReadSet, groups: Sequence[Sequence[int]], algorithm: int = 1,
-               want_msa: bool = True, scores=None):
+               want_msa: bool = True, scores=None, as_array: bool = False):
     """Align every group (list of read indices, in alignment order) into its own graph.
 
-    Returns (consensus list, msa list (list of row strings per group), stats dict)."""
+    Returns (consensus list, msa list (list of row strings per group), stats dict).  With
+    ``as_array`` every MSA is a (rows, cols) uint8 array of characters instead of strings
+    (views into one buffer: no per-row decoding)."""
     sc = dict(DEFAULT_SCORES)
     if scores:
         sc.update(scores)
@@ -54,7 +56,10 @@ def poa_groups(ctx: Context, reads: ReadSet, groups: Sequence[Sequence[int]], al
         cons.append(craw[co:co + int(clen[k])].decode())
         co += int(clen[k])
         r, c = int(rows[k]), int(cols[k])
-        if want_msa:
+        if want_msa and as_array:
+            msas.append(mbuf[mo:mo + r * c].reshape(r, c))
+            mo += r * c
+        elif want_msa:
             msas.append([mraw[mo + i * c: mo + (i + 1) * c].decode() for i in range(r)])
             mo += r * c
         else:
