@@ -33,7 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before any CUDA context (see svscope_b200/__init__.py)
 
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 10.16e9   # profiles/r01_poa_persistent_kernel_pruned_ncu_full.txt (one launch, 148 alignments)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 15.59e9   # profiles/r01_poa_persistent_kernel_final_ncu_full.txt (one launch, 296 alignments)
 METRIC = "localGraph windows/sec"
 UNIT = "windows/s"
 WORKLOAD = "configs[1]: synthetic INS/DEL windows, 30 tumor + 30 normal reads, 5-15 kb, 5% error"
@@ -314,10 +314,10 @@ def main():
     achieved_gbs = algo_bytes_per_launch / avg_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved_gbs / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (148 alignments, launch 21 of a depth-12 probe: "
-                                "profiles/r01_poa_persistent_kernel_pruned_ncu_full.txt); almost all of it is "
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (296 alignments, launch 14 of a depth-8 probe: "
+                                "profiles/r01_poa_persistent_kernel_final_ncu_full.txt); almost all of it is "
                                 "traceback codes (1-2 B per DP cell), which are implementation traffic, not algorithmic bytes",
-                "kernel": "poa_persistent_kernel<512,8>", "launches_per_step": n_launch,
+                "kernel": "poa_persistent_kernel<256,8>", "launches_per_step": n_launch,
                 "avg_launch_ms": avg_launch_s * 1e3,
                 "note": "algorithmic bytes = read + rank-ordered graph + alignment path (SURVEY 8d); the kernel is "
                         "integer-ALU bound, see roofline_alu; launches of different worker streams overlap, so the "

@@ -221,3 +221,24 @@ def test_full_size_windows_equal_oracle_golden(ctx, golden_dir, name):
     np.random.seed(2023)
     rec = Decision(w[4], w[0], w[1], w[2], w[3])
     assert [str(x) for x in rec] == g["record"]
+
+
+def test_edit_distance_pairs_and_alu_probe(ctx, oracle):
+    """The pair form of the edit-distance entry point, and the integer-ALU probe bench.py uses."""
+    import ctypes
+    from svscope_b200._lib import ReadSet, load, ptr
+    rng = np.random.default_rng(12)
+    base = synth._rand_seq(rng, 1500)
+    seqs = [synth._to_str(synth.noisy_copy(rng, base, 0.08)) for _ in range(5)] + ["", "ACGT"]
+    reads = ReadSet(ctx, seqs)
+    a = np.array([0, 1, 2, 5, 6, 3], np.int64)
+    b = np.array([1, 2, 4, 0, 5, 3], np.int64)
+    dist = np.zeros(len(a), np.int32)
+    stats = np.zeros(5, np.float64)
+    ctx.check(load().svs_edit_distance_pairs(ctx._h, reads._h, ptr(a), ptr(b), len(a), ptr(dist), ptr(stats), 5))
+    expect = [oracle.levenshtein(seqs[i], seqs[j]) for i, j in zip(a, b)]
+    assert dist.tolist() == expect
+    assert dist[5] == 0 and dist[3] == len(seqs[0]) and dist[4] == 4
+    rates = ctx.int_alu_probe()
+    assert rates["max"] > 1000 and rates["addmax"] > 1000      # G thread-operations per second
+    reads.close()
