@@ -38,9 +38,13 @@ int svs_create(int device, svs_ctx** out);
 void svs_destroy(svs_ctx* ctx);
 const char* svs_last_error(const svs_ctx* ctx);
 const char* svs_version(void);
-/* Options (all optional): "poa_threads" CTA size of the alignment kernel (128|256|512),
- * "ring_rows" packed rows kept in shared memory, "workers" host threads that own graphs and
- * streams, "arena_mb" device scratch arena in MiB (0 = 85 % of free memory). */
+/* Options (all optional): "poa_threads" CTA size of the alignment kernel (128|256|512; default
+ * 256), "poa_cols" read columns per thread (4|8|16; default 8), "ring_rows" packed rows kept in
+ * shared memory (default 12), "prune" exact score-bound pruning (default 1), "streams" concurrent
+ * round streams (default 2), "workers" host threads for graph merge/export (default 4),
+ * "arena_mb" device scratch arena in MiB (0 = 85 % of free memory).  The persistent kernel
+ * (per-SM scratch slots, fused traceback, pruning) runs for 256x8 (two CTAs per SM), 512x8,
+ * 512x4 and 256x16; other shapes take the classic one-CTA-per-alignment launch. */
 int svs_set_option(svs_ctx* ctx, const char* key, int64_t value);
 int64_t svs_get_option(const svs_ctx* ctx, const char* key);
 
@@ -76,8 +80,10 @@ int svs_poa_result_copy(const svs_poa_result* res, uint8_t* consensus, uint8_t* 
  * [3] sum of traceback-kernel ms, [4] wall ms of the call, [5] launches of the DP kernel,
  * [6] launches of the traceback kernel, [7] bytes host->device, [8] bytes device->host,
  * [9] algorithmic bytes (read + graph + path), [10] exported rows,
- * [11] graph rows total, [12..15] host ms summed over workers: waiting for the device,
- * merging paths into graphs, exporting rank-ordered graphs, packing the staging buffer */
+ * [11] graph rows total, [12..15] host ms: waiting for the device, merging paths into graphs,
+ * exporting rank-ordered graphs, packing the staging buffer, [18] ms spent issuing launches,
+ * [22] D2H ms on the streams, [23] pruning retries (alignments repeated because the guessed
+ * score bound was too high) */
 int svs_poa_result_stats(const svs_poa_result* res, double* stats, int n_stats);
 void svs_poa_result_free(svs_poa_result* res);
 

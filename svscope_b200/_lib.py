@@ -54,8 +54,6 @@ def load():
                     "(there is no CPU fallback)")
             L = ctypes.CDLL(LIB_PATH)
             for name, (res, args) in SYMBOLS.items():
-                if not hasattr(L, name) and os.environ.get("SVS_DEV_PARTIAL") == "1":
-                    continue  # development only: library built before every kernel existed
                 fn = getattr(L, name)
                 fn.restype = res
                 fn.argtypes = args

@@ -3,6 +3,7 @@
 // (poa_cell.h) with the same information loss as the kernels (predecessor rows are only
 // visible as packed words; E opened from A), so that the algorithmic equivalence with the
 // oracle's five-matrix equality traceback can be checked without a GPU.  Not shipped.
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -285,6 +286,16 @@ int64_t emu_last_alignment(void* h, int32_t* nodes, int32_t* pos, int64_t cap) {
   const int64_t n = static_cast<int64_t>(e->last.size() / 2);
   for (int64_t k = 0; k < n && k < cap; ++k) { nodes[k] = e->last[2 * k]; pos[k] = e->last[2 * k + 1]; }
   return n;
+}
+// merge a given alignment without running the DP (host-graph micro-benchmarks)
+void emu_add_pairs(void* h, const int32_t* nodes, const int32_t* pos, int64_t n, const uint8_t* seq, int64_t len) {
+  static_cast<Emu*>(h)->graph.add_alignment(nodes, pos, static_cast<size_t>(n), seq, static_cast<uint32_t>(len));
+}
+double emu_time_export(void* h, int reps) {
+  Emu* e = static_cast<Emu*>(h);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int k = 0; k < reps; ++k) e->graph.export_ranked(e->sc, 12, &e->rg);
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
 }
 int64_t emu_num_nodes(void* h) { return static_cast<Emu*>(h)->graph.num_nodes(); }
 void emu_rank_to_node(void* h, int32_t* out) {
