@@ -12,10 +12,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def ctx():
+    # the process-wide default context (also used by spoa.poa / Decision / EMCluster): one device
+    # arena for the whole test session instead of one per context
     from svscope_b200 import _lib
-    c = _lib.Context(0)
-    yield c
-    c.close()
+    return _lib.Context.default(0)
 
 
 def _random_group(rng, it, lmax=400):
