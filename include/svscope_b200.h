@@ -139,6 +139,23 @@ int svs_edit_distance_pairs(svs_ctx* ctx, const svs_reads* reads, const int64_t*
                             const int64_t* b, int64_t n_pairs, int32_t* dist, double* stats,
                             int n_stats);
 
+/* ---- MisScore alignments (the step after the Raw.bed) -------------------
+ * Replaces the per-pair Biopython call of src/PairwiseCompare.py:19-30
+ *   pairwise2.align.globalms(Som, Ger, 1, 0, -1, -1)[0]  ->  MisScore = columns - '|' columns
+ * (callers src/PairwiseCompare.py:54-64 CalculateMisscore, :77-88 MisScorePipe, src/SVscope.py:282).
+ * Pair k aligns reads a[k] (seqA, rows) and b[k] (seqB, columns); integer scores with
+ * open == extend <= 0 (anything else: SVS_ERR_UNSUPPORTED), empty sequences: SVS_ERR_ARG
+ * (globalms returns no alignment, the reference's [0] raises).  The alignment is the first
+ * one of pairwise2's traversal order (gap in seqA before match/mismatch before gap in seqB).
+ * out[4k..4k+3] = score, alignment columns, columns with equal symbols, MisScore.
+ * lines (optional): match line of each alignment ('|' equal, '.' different, ' ' gap) at
+ * lines[line_off[k]], capacity la+lb bytes each.  stats (optional): DP cells, kernel ms,
+ * launches, trace bytes written. */
+int svs_misscore_pairs(svs_ctx* ctx, const svs_reads* reads, const int64_t* a, const int64_t* b,
+                       int64_t n_pairs, int match, int mismatch, int open, int extend,
+                       int32_t* out, uint8_t* lines, const int64_t* line_off, double* stats,
+                       int n_stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,9 @@ Pinning status
   (oracle/spoa_oracle.cpp); the wheel is absent and the reference has no vectors for it.
 * Levenshtein (``levenshtein``): **parity unpinned** — textbook DP; module absent, no live
   reference call site (src/DecisionMaker.py:34,76-84 are comments).
+* MisScore (``pairwise_first_alignment``, ``aligment_score``, ``calculate_misscore``): **parity
+  unpinned** — restates Bio.pairwise2 (absent; src/PairwiseCompare.py:8-11,19-64) from
+  recollection: oracle/pairwise2_oracle.py (literal, strings) and oracle/misscore_oracle.c.
 * Feature selection, mixture model, Decision (``msa_feature_selection``, ``em_cluster``,
   ``decision``): **pinned** against the reference's own Python (`src/DataScanner.py`,
   `src/ReadsCluster.py`, `src/DecisionMaker.py`) imported unmodified in the build container by
@@ -33,7 +36,9 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile oracle/_build/liboracle.so with the committed Makefile."""
-    if force or not os.path.exists(_LIB_PATH):
+    srcs = [os.path.join(_HERE, f) for f in ("spoa_oracle.cpp", "lev_oracle.c", "misscore_oracle.c", "Makefile")]
+    stale = not os.path.exists(_LIB_PATH) or any(os.path.getmtime(f) > os.path.getmtime(_LIB_PATH) for f in srcs)
+    if force or stale:
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
                        stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -72,6 +77,9 @@ def lib():
         L.lev_myers.restype = ctypes.c_int64
         L.lev_myers.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_char_p, ctypes.c_int64]
         L.lev_matrix.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
+        L.pw2_first.restype = ctypes.c_int64
+        L.pw2_first.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int,
+                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -480,3 +488,50 @@ def tdscope_npz(TDRecord, sequenceList, ReadIDs, flank_5, flank_3):
 def format_record(rec) -> str:
     """Raw.bed line as written at SVscope.py:175."""
     return "\t".join(str(x) for x in rec) + "\n"
+
+
+# --------------------------------------------------------------------------------------
+# MisScore  (next row F1: src/PairwiseCompare.py:19-64; Bio.pairwise2 restated, parity unpinned)
+def pairwise_first_alignment(a: str, b: str, match: int = 1, mismatch: int = 0, open: int = -1,
+                             extend: int = -1, want_line: bool = False):
+    """First alignment of ``pairwise2.align.globalms(a, b, match, mismatch, open, extend)``:
+    dict(score, length, matches, pops[, line]).  IndexError on empty input, like ``[...][0]``."""
+    ab, bb = a.encode(), b.encode()
+    out = np.zeros(4, np.int64)
+    line = ctypes.create_string_buffer(len(ab) + len(bb) + 1) if want_line else None
+    rc = lib().pw2_first(ab, len(ab), bb, len(bb), match, mismatch, open, extend, out.ctypes.data, line)
+    if rc == -2:
+        raise IndexError("list index out of range")
+    if rc != 0:
+        raise MemoryError("pw2_first")
+    res = dict(score=int(out[0]), length=int(out[1]), matches=int(out[2]), pops=int(out[3]))
+    if want_line:
+        res["line"] = line.raw[:res["length"]].decode()
+    return res
+
+
+def aligment_score(SomConsensus: str, GerConsensus: str, cutoff: int = 0) -> int:
+    """PairwiseCompare.py:19-30 (spelling of the reference kept)."""
+    if cutoff == 0:
+        r = pairwise_first_alignment(SomConsensus, GerConsensus)
+        return r["length"] - r["matches"]
+    alig = pairwise_first_alignment(SomConsensus, GerConsensus, want_line=True)["line"]
+    td = alig[cutoff:len(alig) - cutoff]
+    return len(td) - td.count("|")
+
+
+def smaller_absolute_value(a, b):
+    """PairwiseCompare.py:32-36."""
+    return a if abs(a) < abs(b) else b
+
+
+def calculate_misscore(somSeqList: str, germSeqList: str):
+    """PairwiseCompare.py:54-64 on the two ';'-joined consensus columns of a Raw.bed row."""
+    mis = 1000000000000000000000
+    for som in somSeqList.split(";"):
+        for ger in germSeqList.split(";"):
+            score = aligment_score(som, ger)
+            if len(som) < len(ger):
+                score = (-1) * score
+            mis = smaller_absolute_value(mis, score)
+    return mis

@@ -40,6 +40,7 @@ SYMBOLS = {
     "svs_em_batch": (ctypes.c_int, [c_vp, ctypes.c_int64] + [c_vp] * 7 + [ctypes.c_int32, c_vp, ctypes.c_int32] + [c_vp] * 9),
     "svs_edit_distance_matrix": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, c_vp, c_vp, c_vp, ctypes.c_int]),
     "svs_edit_distance_pairs": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, c_vp, c_vp, ctypes.c_int]),
+    "svs_misscore_pairs": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64] + [ctypes.c_int] * 4 + [c_vp] * 4 + [ctypes.c_int]),
 }
 
 

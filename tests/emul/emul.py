@@ -95,3 +95,38 @@ class EmuSession:
         if self.h:
             lib().emu_free(self.h)
             self.h = None
+
+
+# --------------------------------------------------------------------------------------
+# MisScore kernel emulation (misscore_emul.cpp)
+MIS_LIB = os.path.join(HERE, "_build", "libmisscore_emul.so")
+_mis = None
+
+
+def mis_lib():
+    global _mis
+    if _mis is None:
+        src = os.path.join(HERE, "misscore_emul.cpp")
+        deps = [src] + [os.path.join(ROOT, "svscope_b200", "csrc", h) for h in ("misscore_cell.h", "misscore_tb.h")]
+        if not os.path.exists(MIS_LIB) or any(os.path.getmtime(d) > os.path.getmtime(MIS_LIB) for d in deps):
+            os.makedirs(os.path.dirname(MIS_LIB), exist_ok=True)
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", src, "-o", MIS_LIB], check=True)
+        L = ctypes.CDLL(MIS_LIB)
+        L.mis_emul.restype = ctypes.c_int
+        L.mis_emul.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
+                               ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                               ctypes.c_void_p]
+        _mis = L
+    return _mis
+
+
+def misscore_emul(a: str, b: str, match=1, mismatch=0, gap=1, threads=256, cols=16, want_line=False):
+    """dict(score, length, matches, status[, line]) from the emulated kernel."""
+    ab, bb = a.encode(), b.encode()
+    out = np.zeros(4, np.int32)
+    line = ctypes.create_string_buffer(len(ab) + len(bb) + 1) if want_line else None
+    rc = mis_lib().mis_emul(ab, len(ab), bb, len(bb), match, mismatch, gap, threads, cols, out.ctypes.data, line)
+    res = dict(score=int(out[0]), length=int(out[1]), matches=int(out[2]), status=int(rc))
+    if want_line:
+        res["line"] = line.raw[:res["length"]].decode()
+    return res
