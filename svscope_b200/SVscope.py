@@ -31,40 +31,82 @@ def raw_bed_name(TSampleID: str, NSampleID: str) -> str:
     return "%s.vs.%s.TandemRepeat.Raw.bed" % ("-".join(TSampleID.split(",")), "-".join(NSampleID.split(",")))
 
 
+def _format(rec) -> str:
+    return "\t".join([str(x) for x in rec]) + "\n"
+
+
 def write_raw_bed(path: str, records, append: bool = False) -> None:
     with open(path, "a" if append else "w") as f:
         for rec in records:
-            f.write("\t".join([str(x) for x in rec]) + "\n")
+            f.write(_format(rec))
     os.system("sort -k1,1 -k2,2n {p} -o {p}".format(p=path))
 
 
-def run_windows(windows, batch_windows: int = BATCH_WINDOWS, **kw):
-    """Records for a list of windows, sharded over the ranks of the current process group."""
+def _ranks():
     import torch.distributed as dist
-    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-    if distributed:
-        mine = _shard.my_shard([window_cost(w) for w in windows], dist.get_rank(), dist.get_world_size())
-    else:
-        mine = list(range(len(windows)))
-    local = []
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _my_indices(windows):
+    rank, world = _ranks()
+    if world == 1:
+        return list(range(len(windows)))
+    return _shard.my_shard([window_cost(w) for w in windows], rank, world)
+
+
+def iter_batches(windows, mine, batch_windows: int = BATCH_WINDOWS, **kw):
+    """Yields (window indices, records) of one GPU batch after the other."""
     for b in range(0, len(mine), batch_windows):
-        chunk = [windows[i] for i in mine[b:b + batch_windows]]
-        local.extend(localgraph_batch(chunk, **kw).records)
-    if not distributed:
+        idx = mine[b:b + batch_windows]
+        yield idx, localgraph_batch([windows[i] for i in idx], **kw).records
+
+
+def run_windows(windows, batch_windows: int = BATCH_WINDOWS, **kw):
+    """Records for a list of windows, sharded over the ranks of the current process group
+    (the full list on rank 0, None on the other ranks)."""
+    mine = _my_indices(windows)
+    local = []
+    for _, recs in iter_batches(windows, mine, batch_windows, **kw):
+        local.extend(recs)
+    if _ranks()[1] == 1:
         return local
     return _shard.gather_records(mine, local, len(windows), group=_shard.host_group())
 
 
+def _finished_records(paths):
+    done = set()
+    for p in paths:
+        if os.path.exists(p):
+            with open(p) as fh:
+                done.update("\t".join(x.strip().split("\t")[0:3]) for x in fh.readlines() if x.strip())
+    return done
+
+
 def localGraph_npz(args):
     """Reference :185-239: all ``*.npz`` batches in ``args.savedir`` -> Raw.bed; ``--Continue``
-    skips windows whose TDRecord is already in the output."""
+    skips windows whose TDRecord is already in the output (:195-200, :213).
+
+    The records of every GPU batch are appended at once to ``<Raw.bed>.part<rank>`` (flushed to
+    disk), and the parts are merged into the sorted Raw.bed at the end, so an interrupted run
+    loses at most the batch in flight: ``--Continue`` also counts what the parts hold."""
+    import glob
+    import torch.distributed as dist
     logging.info("Local Graph : Start working")
     t0 = time.time()
+    rank, world = _ranks()
+    group = _shard.host_group() if world > 1 else None
     path = os.path.join(args.savedir, raw_bed_name(args.TSampleID, args.NSampleID))
-    finished = set()
-    if getattr(args, "Continue", False) and os.path.exists(path):
-        with open(path) as fh:
-            finished = {"\t".join(x.strip().split("\t")[0:3]) for x in fh.readlines()}
+    resume = bool(getattr(args, "Continue", False))
+    if rank == 0 and not resume:
+        for stale in glob.glob(glob.escape(path) + ".part*"):
+            os.remove(stale)
+    if world > 1:
+        dist.barrier(group=group)
+    finished = _finished_records([path] + sorted(glob.glob(glob.escape(path) + ".part*"))) if resume else set()
+    if world > 1:
+        dist.barrier(group=group)  # every rank has read the parts before anyone appends
     windows = []
     for name in sorted(os.listdir(args.savedir)):
         if not re.search("npz", name):
@@ -75,9 +117,23 @@ def localGraph_npz(args):
             if finished and row[4] in finished:
                 continue
             windows.append(row)
-    records = run_windows(windows)
-    if records is not None:
-        write_raw_bed(path, records, append=bool(finished))
+    mine = _my_indices(windows)
+    with open(path + ".part%d" % rank, "a") as part:
+        for _, recs in iter_batches(windows, mine, BATCH_WINDOWS):
+            part.write("".join(_format(r) for r in recs))
+            part.flush()
+            os.fsync(part.fileno())
+    if world > 1:
+        dist.barrier(group=group)
+    if rank == 0:
+        parts = sorted(glob.glob(glob.escape(path) + ".part*"))
+        with open(path, "a" if resume else "w") as out:
+            for p in parts:
+                with open(p) as fh:
+                    out.write(fh.read())
+        os.system("sort -k1,1 -k2,2n {p} -o {p}".format(p=path))
+        for p in parts:
+            os.remove(p)
     logging.info(f"Local Graph : work finished with {(time.time() - t0) / 3600} hour")
     return path
 

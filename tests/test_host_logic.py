@@ -144,3 +144,93 @@ def test_synth_formats(tmp_path):
     assert back[0][4] == w[4] and list(back[0][1]) == list(w[1]) and back[0][0] == w[0]
     a, b = synth.make_c2_window(5), synth.make_c2_window(5)
     assert a[0] == b[0] and a[4] == b[4]
+
+
+def test_raw_bed_streaming_writer_resumes(tmp_path, monkeypatch):
+    """localGraph_npz appends every batch to a part file; after an interruption --Continue
+    computes only the missing windows and the merged Raw.bed is complete and sorted
+    (reference --Continue: src/SVscope.py:195-200,213).  The GPU batch call is replaced by a
+    stand-in: this is the host-side writer only."""
+    import argparse
+    import types
+    from svscope_b200 import SVscope, synth
+    wins = []
+    for k in range(7):
+        w = synth.make_small_window(30 + k, body_len=60, sv_len=20, n_tumor=3, n_normal=3, n_carriers=2)
+        w[4] = "chr%d\t%d\t%d" % (1 + k % 2, 1000 * (7 - k), 1000 * (7 - k) + 60)
+        wins.append(w)
+    synth.save_npz(str(tmp_path / "T.vs.N.TandemRepeat.batch0.npz"), wins)
+    calls = []
+
+    def fake_batch(chunk, **kw):
+        calls.append([w[4] for w in chunk])
+        if fail["on"] == len(calls):
+            raise RuntimeError("interrupted")
+        return types.SimpleNamespace(records=[w[4].split("\t") + ["s", "i", 1, "g", "j", 2, "NormalOutput"] for w in chunk])
+
+    fail = {"on": 3}
+    monkeypatch.setattr(SVscope, "localgraph_batch", fake_batch)
+    monkeypatch.setattr(SVscope, "BATCH_WINDOWS", 2)
+    args = argparse.Namespace(savedir=str(tmp_path), TSampleID="T", NSampleID="N", Continue=False)
+    with pytest.raises(RuntimeError):
+        SVscope.localGraph_npz(args)
+    out = tmp_path / SVscope.raw_bed_name("T", "N")
+    part = tmp_path / (SVscope.raw_bed_name("T", "N") + ".part0")
+    assert not out.exists() and len(part.read_text().splitlines()) == 4     # two batches reached the disk
+    fail["on"] = -1
+    calls.clear()
+    args.Continue = True
+    SVscope.localGraph_npz(args)
+    assert sorted(sum(calls, [])) == sorted(w[4] for w in wins[4:])           # only the missing windows
+    lines = out.read_text().splitlines()
+    assert len(lines) == 7 and not part.exists()
+    keys = [(x.split("\t")[0], int(x.split("\t")[1])) for x in lines]
+    assert keys == sorted(keys) and all(len(x.split("\t")) == 10 for x in lines)
+    # a fresh run (no --Continue) rewrites the file from scratch
+    calls.clear()
+    args.Continue = False
+    SVscope.localGraph_npz(args)
+    assert len(sum(calls, [])) == 7 and len(out.read_text().splitlines()) == 7
+
+
+def _npz_worker(rank, world, port, savedir):
+    import argparse
+    import types
+    import torch.distributed as dist
+    from svscope_b200 import SVscope
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    SVscope.localgraph_batch = lambda chunk, **kw: types.SimpleNamespace(
+        records=[w[4].split("\t") + ["s", "i", 1, "g", "rank%d" % rank, 2, "NormalOutput"] for w in chunk])
+    SVscope.BATCH_WINDOWS = 2
+    SVscope.localGraph_npz(argparse.Namespace(savedir=savedir, TSampleID="T", NSampleID="N", Continue=False))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_raw_bed_writer_gloo(tmp_path):
+    """N>1 path of localGraph_npz on CPU: two ranks shard the windows, append to their own
+    parts, rank 0 merges and sorts (the GPU batch call is a stand-in)."""
+    import torch.multiprocessing as mp
+    from svscope_b200 import SVscope
+    wins = []
+    for k in range(9):
+        w = synth.make_small_window(50 + k, body_len=40 + 5 * k, sv_len=10, n_tumor=3, n_normal=3, n_carriers=2)
+        w[4] = "chr%d\t%d\t%d" % (1 + k % 3, 500 * (9 - k), 500 * (9 - k) + 40)
+        wins.append(w)
+    synth.save_npz(str(tmp_path / "b.npz"), wins)
+    ctx = mp.get_context("spawn")
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_npz_worker, args=(r, 2, port, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    lines = (tmp_path / SVscope.raw_bed_name("T", "N")).read_text().splitlines()
+    assert len(lines) == 9
+    keys = [(x.split("\t")[0], int(x.split("\t")[1])) for x in lines]
+    assert keys == sorted(keys)
+    assert {x.split("\t")[7] for x in lines} == {"rank0", "rank1"}
+    assert not [f for f in os.listdir(tmp_path) if ".part" in f]
