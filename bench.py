@@ -357,6 +357,23 @@ def main():
                           "gcups": st["ed_cells"] / max(st["ed_ms"], 1e-9) / 1e6},
         "em_output_windows": sum(r[-1].endswith("EMOutput") for r in out.records),
     }
+    # informational, outside the timed region: the step after the Raw.bed,
+    # MisScore alignments of the records this step produced
+    try:
+        from svscope_b200 import PairwiseCompare as PC
+        mpairs = [p for r in out.records if str(r[9]) == "NormalOutput|EMOutput"
+                  for p in PC._record_pairs(str(r[3]), str(r[6]))]
+        mst = {}
+        t_m = time.perf_counter()
+        PC.misscore_pairs(mpairs, ctx=ctx, stats=mst)
+        t_m = time.perf_counter() - t_m
+        line["misscore_after_step"] = {"pairs": len(mpairs), "cells": mst.get("cells", 0.0),
+                                       "kernel_ms": mst.get("kernel_ms", 0.0), "wall_s": t_m,
+                                       "gcups_kernel": mst.get("cells", 0.0) / max(mst.get("kernel_ms", 0.0), 1e-9) / 1e6,
+                                       "note": "not part of `value`: PairwiseCompare.MisScorePipe's alignments "
+                                               "(svs_misscore_pairs) on the records of the last step"}
+    except Exception as exc:  # informational only
+        line["misscore_after_step"] = {"error": repr(exc)}
     if not args.no_cpu_baseline and world == 1:
         cb = run_cpu(windows, args.cpu_budget)
         line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port",
