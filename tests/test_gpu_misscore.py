@@ -134,3 +134,29 @@ def test_errors_are_loud(ctx):
     with pytest.raises(IndexError):
         CalculateMisscore({"somSeqList": "ACGT;", "germSeqList": "ACGT"})
     assert misscore_pairs([], ctx=ctx).shape == (0, 4)
+
+
+def test_small_arena_runs_in_rounds_and_reports_capacity(oracle):
+    """A context with a 48 MiB arena: 120 pairs of ~2 kb (1-2 MiB of trace each) need several
+    launches and still equal the oracle; a pair whose trace does not fit is an error, not a
+    silent truncation."""
+    from svscope_b200 import _lib
+    from svscope_b200.PairwiseCompare import misscore_pairs
+    small = _lib.Context(0, arena_mb=48)
+    try:
+        rng = random.Random(31)
+        pairs = []
+        for _ in range(120):
+            a = "".join(rng.choice("ACGT") for _ in range(rng.randint(1500, 2200)))
+            pairs.append((a, _mutate(rng, a, 0.04)))
+        stats = {}
+        out = misscore_pairs(pairs, ctx=small, stats=stats)
+        assert stats["launches"] >= 3
+        for k in (0, 17, 63, 119):
+            r = oracle.pairwise_first_alignment(*pairs[k])
+            assert tuple(out[k][:3]) == (r["score"], r["length"], r["matches"])
+        big = "".join(rng.choice("ACGT") for _ in range(12000))
+        with pytest.raises(_lib.SvsError, match="MiB of trace"):
+            misscore_pairs([(big, big)], ctx=small)
+    finally:
+        small.close()
