@@ -79,27 +79,17 @@ def AligmentScore(SomConsensus, GerConsensus, cutoff=0):
 
 
 def smaller_absolute_value(a, b):
-    """:32-36"""
-    if abs(a) < abs(b):
-        return a
-    return b
+    """:32-36 — ``a`` only if strictly smaller in absolute value (ties go to ``b``)."""
+    return a if abs(a) < abs(b) else b
 
 
 def Mismatch_abs(callLine):
-    """:38-52, including its quirk: ``Abs`` is never updated, so every entry is the length
-    difference to the LAST germline consensus."""
-    somSeqList = callLine['somSeqList'].split(';')
-    germSeqList = callLine['germSeqList'].split(';')
-    Res = []
-    for Som in somSeqList:
-        Abs = 1000000000000000000000
-        for Ger in germSeqList:
-            score = len(Som) - len(Ger)
-            AbsScore = smaller_absolute_value(Abs, score)
-        Res.append(AbsScore)
-    if len(Res) > 1:
-        return ';'.join(list(map(str, Res)))
-    return str(Res[0])
+    """:38-52.  The reference compares every length difference with a constant that is never
+    updated, so each entry ends up as len(somatic consensus) - len(LAST germline consensus);
+    that is what is returned here (one number, or ';'-joined for several somatic consensus)."""
+    last_germ = callLine['germSeqList'].split(';')[-1]
+    diffs = [smaller_absolute_value(10 ** 21, len(som) - len(last_germ)) for som in callLine['somSeqList'].split(';')]
+    return ';'.join(str(d) for d in diffs)
 
 
 def _record_pairs(somSeqList: str, germSeqList: str):
@@ -127,15 +117,14 @@ def CalculateMisscore(callLine):
 
 
 def CallAlleleFreq(SomaticTD):
-    """:66-75.  ``re.search('_tumor|', x)`` matches every ID (empty alternative), so all
-    germline-cluster reads count in the denominator - kept, it is the reference's behaviour."""
-    som = SomaticTD['somSupportReadID']
-    germ = SomaticTD['germSupportReadID']
-    somReadCountList = np.array([len(x.split(",")) for x in som.split(";")])
-    germReadList = np.concatenate([x.split(",") for x in germ.split(";")])
-    germTumorReads = [x for x in germReadList if re.search('_tumor|', x)]
-    N = np.sum(somReadCountList) + len(germTumorReads)
-    return ";".join([str(x) for x in somReadCountList / N])
+    """:66-75: per somatic cluster, reads / (all somatic reads + germline-cluster reads).  The
+    reference filters the germline reads with ``re.search('_tumor|', x)``, whose empty
+    alternative matches every ID, so ALL germline-cluster reads count - kept as is."""
+    som_counts = np.array([len(ids.split(",")) for ids in SomaticTD['somSupportReadID'].split(";")])
+    germ_reads = [rid for ids in SomaticTD['germSupportReadID'].split(";") for rid in ids.split(",")]
+    counted = [rid for rid in germ_reads if re.search('_tumor|', rid)]
+    total = np.sum(som_counts) + len(counted)
+    return ";".join(str(x) for x in som_counts / total)
 
 
 def MisScorePipe(filepath, stats: dict | None = None):
@@ -166,19 +155,17 @@ def MisScorePipe(filepath, stats: dict | None = None):
 
 
 def main(args):
-    """:90-97"""
-    filepath = os.path.join(args.workDir, args.sampleID,
-                            "%s.vs.%s.TandemRepeat.Raw.bed" % (args.sampleID, args.sampleID))
-    output = os.path.join(args.outputDir, '%s.Somatic.bed' % args.sampleID)
-    if not os.path.exists(args.outputDir):
-        os.makedirs(args.outputDir)
-    SomaticRes = MisScorePipe(filepath)
-    SomaticRes.to_csv(output, sep="\t", header=None, index=False)
+    """:90-97: <workDir>/<sample>/<sample>.vs.<sample>.TandemRepeat.Raw.bed -> <outputDir>/<sample>.Somatic.bed"""
+    sample = args.sampleID
+    raw_bed = os.path.join(args.workDir, sample, "%s.vs.%s.TandemRepeat.Raw.bed" % (sample, sample))
+    os.makedirs(args.outputDir, exist_ok=True)
+    MisScorePipe(raw_bed).to_csv(os.path.join(args.outputDir, '%s.Somatic.bed' % sample), sep="\t", header=None,
+                                 index=False)
 
 
 if __name__ == "__main__":
-    parser = argparse.ArgumentParser(add_help=True)
-    parser.add_argument("-w", "--workDir", required=True, help="work Dir")
-    parser.add_argument("-s", "--sampleID", required=True, help="sampleID")
-    parser.add_argument("-o", "--outputDir", required=True, help="output dir")
-    main(parser.parse_args())
+    cli = argparse.ArgumentParser(description=__doc__)
+    cli.add_argument("-w", "--workDir", required=True, help="directory holding <sampleID>/...Raw.bed")
+    cli.add_argument("-s", "--sampleID", required=True)
+    cli.add_argument("-o", "--outputDir", required=True)
+    main(cli.parse_args())
