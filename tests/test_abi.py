@@ -49,3 +49,14 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src, f
+
+
+def test_scripts_do_not_use_the_oracle():
+    """Only tests/, smoke() and bench.py's CPU legs may touch oracle/: the probes that compare
+    against it live in tests/tools/."""
+    sdir = os.path.join(ROOT, "scripts")
+    for dirpath, _, files in os.walk(sdir):
+        for f in files:
+            if f.endswith((".py", ".sh", ".cu")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

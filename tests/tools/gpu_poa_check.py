@@ -1,6 +1,6 @@
 """First GPU bring-up: alignment pairs / MSA / consensus of the CUDA path vs the oracle."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import oracle as O
 from svscope_b200 import synth, _lib

@@ -3,7 +3,7 @@ POA: per read length a small batch of identical-size windows (reference + 10 noi
 edit distance: 256 pairs per length at 10 % divergence.  GCUPS on nominal cells, next to the
 CPU oracle on the sizes it finishes quickly.  Writes gpurun_out/kernel_sweep.json."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import oracle as O
 from svscope_b200 import synth, _lib

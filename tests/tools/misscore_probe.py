@@ -2,7 +2,7 @@
 svs_misscore_pairs, kernel time from the library's CUDA events, end-to-end time with host
 strings in and counts out, and the oracle on one core for a few pairs.
 
-    python scripts/misscore_probe.py [--pairs 592] > gpurun_out/misscore_probe.json
+    python tests/tools/misscore_probe.py [--pairs 592] > gpurun_out/misscore_probe.json
 """
 import argparse
 import json
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 
 def make_pairs(n, seed=1):
