@@ -147,11 +147,28 @@ def localGraph(args):
         "accelerated path; use localGraph_npz on npz batches written by SomTDDetector_AimDatFetch.py")
 
 
+def somatic_bed(rawBedFile: str, savedir: str, TSampleID: str) -> str:
+    """The MisScore head of the reference's ``AlnFeature`` (src/SVscope.py:282-286):
+    ``PairwiseCompare.MisScorePipe(rawBedFile).drop_duplicates()`` plus the ``ABSMisScore``
+    column, written to ``<savedir>/<T>.Somatic.bed`` (tab-separated, no header, no index).  The
+    alignments run on the GPU (svs_misscore_pairs); the rest of AlnFeature (bed.gz/sqlite
+    coverage and mapQ features, random forest) is the reference's and reads this file."""
+    from . import PairwiseCompare
+    df = PairwiseCompare.MisScorePipe(rawBedFile).drop_duplicates()
+    df['ABSMisScore'] = df['MisScore'].apply(lambda x: abs(x))
+    out = os.path.join(savedir, '%s.Somatic.bed' % TSampleID)
+    df.to_csv(out, sep="\t", index=False, header=None)
+    return out
+
+
 def callsomaticSV(args):
-    """Reference :341-356 = localGraph + AlnFeature.  Only the localGraph half is accelerated;
-    when ``args.savedir`` holds npz batches it is run here and the Raw.bed path is returned for
-    the reference's unchanged AlnFeature / OutVCF stages."""
-    return localGraph_npz(args)
+    """Reference :341-356 = localGraph + AlnFeature.  The localGraph half (npz batches in
+    ``args.savedir``) and the MisScore head of AlnFeature run here; the Raw.bed path is returned
+    for the reference's remaining AlnFeature / OutVCF stages."""
+    path = localGraph_npz(args)
+    if _ranks()[0] == 0 and os.path.exists(path) and os.path.getsize(path) > 0:
+        somatic_bed(path, args.savedir, args.TSampleID)
+    return path
 
 
 def main(argv=None):

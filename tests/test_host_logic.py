@@ -234,3 +234,43 @@ def test_two_rank_raw_bed_writer_gloo(tmp_path):
     assert keys == sorted(keys)
     assert {x.split("\t")[7] for x in lines} == {"rank0", "rank1"}
     assert not [f for f in os.listdir(tmp_path) if ".part" in f]
+
+
+def test_callsomaticsv_writes_somatic_bed(tmp_path, monkeypatch, oracle):
+    """callsomaticSV = localGraph_npz + the MisScore head of AlnFeature (src/SVscope.py:282-286):
+    <T>.Somatic.bed holds MisScorePipe's columns plus ABSMisScore.  GPU calls are stand-ins
+    (batch records from the golden Raw.bed, alignments from the oracle): host glue only."""
+    import argparse
+    import json
+    import types
+    from svscope_b200 import SVscope, PairwiseCompare as PC
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "misscore_pipe.json")))
+    rows = [ln.split("\t") for ln in gold["raw_bed"].splitlines()]
+    wins = []
+    for k, r in enumerate(rows):
+        w = synth.make_small_window(80 + k, body_len=40, sv_len=10, n_tumor=3, n_normal=3, n_carriers=2)
+        w[4] = "\t".join(r[:3])
+        wins.append(w)
+    synth.save_npz(str(tmp_path / "b.npz"), wins)
+    by_key = {"\t".join(r[:3]): r for r in rows}
+    monkeypatch.setattr(SVscope, "localgraph_batch",
+                        lambda chunk, **kw: types.SimpleNamespace(records=[by_key[w[4]] for w in chunk]))
+
+    def fake_pairs(pairs, *a, stats=None, **kw):
+        out = np.zeros((len(pairs), 4), np.int32)
+        for k, (x, y) in enumerate(pairs):
+            r = oracle.pairwise_first_alignment(x, y)
+            out[k] = (r["score"], r["length"], r["matches"], r["length"] - r["matches"])
+        return out
+
+    monkeypatch.setattr(PC, "misscore_pairs", fake_pairs)
+    args = argparse.Namespace(savedir=str(tmp_path), TSampleID="T", NSampleID="N", Continue=False)
+    raw = SVscope.callsomaticSV(args)
+    assert sorted(open(raw).read().splitlines()) == sorted(gold["raw_bed"].splitlines())
+    got = [ln.split("\t") for ln in (tmp_path / "T.Somatic.bed").read_text().splitlines()]
+    want = {g[3]: g for g in gold["rows"]}
+    assert len(got) == len(want)
+    for g in got:
+        w = want[g[3]]
+        assert g[:3] == [str(w[0]), str(w[1]), str(w[2])] and g[4:6] == [w[4], w[5]]
+        assert int(g[6]) == w[6] and g[7] == w[7] and int(g[8]) == abs(w[6])
