@@ -102,3 +102,32 @@ def test_levenshtein_bitparallel_equals_dp(oracle):
     m = oracle.levenshtein_matrix(seqs)
     assert np.array_equal(m, m.T) and (np.diag(m) == 0).all()
     assert m[1, 4] == oracle.levenshtein(seqs[1], seqs[4])
+
+
+def test_levenshtein_agrees_with_an_independent_engine(oracle):
+    """The reference's Levenshtein module is absent (parity stays unpinned), but the image has
+    the third-party ``regex`` package, whose fuzzy BESTMATCH minimises substitutions +
+    insertions + deletions: an implementation independent of ours gives the same distances on
+    short, similar strings (its search is exponential on dissimilar ones)."""
+    import random
+    regex = pytest.importorskip("regex")
+    rng = random.Random(1)
+    n = 0
+    for _ in range(300):
+        a = "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 12)))
+        b = list(a)
+        for _ in range(rng.randint(0, 3)):
+            r, p = rng.random(), rng.randrange(len(b) + 1)
+            if r < 0.4 and b:
+                b[min(p, len(b) - 1)] = rng.choice("ACGT")
+            elif r < 0.7:
+                b.insert(p, rng.choice("ACGT"))
+            elif b:
+                b.pop(min(p, len(b) - 1))
+        b = "".join(b) or "A"
+        m = regex.fullmatch(r"(?b)(?:%s){e<=6}" % a, b)
+        if m is None:
+            continue
+        n += 1
+        assert sum(m.fuzzy_counts) == oracle.levenshtein(a, b) == oracle.levenshtein(a, b, bitparallel=True)
+    assert n > 250
