@@ -40,6 +40,11 @@ def lib():
         L.emu_msa.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.emu_set_prune.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.emu_set_dyn.argtypes = [ctypes.c_void_p, ctypes.c_double]
+        L.emu_set_dyn_ext.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.emu_static_fraction.restype = ctypes.c_double
+        L.emu_static_fraction.argtypes = [ctypes.c_void_p]
+        L.emu_overflows.restype = ctypes.c_int
+        L.emu_overflows.argtypes = [ctypes.c_void_p]
         L.emu_retries.restype = ctypes.c_int
         L.emu_retries.argtypes = [ctypes.c_void_p]
         L.emu_kept_fraction.restype = ctypes.c_double
@@ -49,8 +54,10 @@ def lib():
 
 
 class EmuSession:
-    def __init__(self, ring_rows=4, prune=0, dyn=None):
+    def __init__(self, ring_rows=4, prune=0, dyn=None, dyn_ext=None):
         self.h = lib().emu_new(ring_rows)
+        if dyn_ext is not None:
+            lib().emu_set_dyn_ext(self.h, int(dyn_ext))
         if prune:
             lib().emu_set_prune(self.h, prune)
         if dyn is not None:

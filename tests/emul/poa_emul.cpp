@@ -18,8 +18,12 @@ struct Emu {
   int prune = 0;         // 0 off, >0: half-width of the first (narrow) pass
   int dyn = 0;           // 1: dynamic score-bound pruning with a guessed lower bound (lb_ratio * L)
   double lb_ratio = 4.0;
+  int dyn_ext = -1;      // -1: provable right extension of every row; >= 0: that many chunks of lookahead,
+                         //     a row whose last computed chunk is still relevant repeats the alignment with more
+  int overflows = 0;
+  bool overflow = false;
   int retries = 0;
-  double kept_cells = 0, all_cells = 0;
+  double kept_cells = 0, all_cells = 0, static_cells = 0;  // static = cells the static score-bound band would keep
   PoaGraph graph;
   PoaScoring sc;
   uint32_t ring_rows = 4;
@@ -35,12 +39,24 @@ static void emu_align(Emu* E, const uint8_t* read, uint32_t L) {
   E->graph.export_ranked(E->sc, E->ring_rows, &E->rg);
   if (E->dyn) {
     int32_t lb = static_cast<int32_t>(E->lb_ratio * L), score = 0;
-    bool ok = emu_align_dyn(E, read, L, lb, &score);
-    if (!ok || score < lb) {   // the guess was above the optimum: repeat with a feasible score (or unpruned)
-      ++E->retries;
-      lb = ok ? score : INT32_MIN;
+    const int ext0 = E->dyn_ext;
+    bool ok = false;
+    for (;;) {
+      E->overflow = false;
       ok = emu_align_dyn(E, read, L, lb, &score);
+      if (E->overflow) {       // lookahead too short somewhere: widen it (at most up to the provable one)
+        ++E->overflows;
+        E->dyn_ext = E->dyn_ext < 64 ? (E->dyn_ext + 1) * 4 : -1;
+        continue;
+      }
+      if (!ok || score < lb) {   // the guess was above the optimum: repeat with a feasible score (or unpruned)
+        ++E->retries;
+        lb = ok ? score : INT32_MIN;
+        continue;
+      }
+      break;
     }
+    E->dyn_ext = ext0;
     return;
   }
   const RankedGraph& G = E->rg;
@@ -181,11 +197,17 @@ static bool emu_align_dyn(Emu* E, const uint8_t* read, uint32_t L, int32_t lb, i
     const int64_t slack = static_cast<int64_t>(s.m) * L - lb;
     const int64_t dmax = slack <= 0 ? 0 : slack / (s.m - s.c) + 1;
     ext = static_cast<int>(std::min<int64_t>(nchunk, dmax / C + 2));
+    if (E->dyn_ext >= 0) ext = std::min(ext, E->dyn_ext);
   }
+  const bool lookahead = have_lb && E->dyn_ext >= 0;
   int32_t best = INT32_MIN; uint32_t best_row = 0;
   const int32_t* dp = G.depth.data();
   for (uint32_t i = 1; i <= R; ++i) {
     P[i * W] = pack_cell(G.h0[i], kNeg, kNeg);
+    if (have_lb)
+      for (uint32_t j = 1; j <= L; ++j)
+        E->static_cells += cell_bound(s, dp[4 * i], dp[4 * i + 1], dp[4 * i + 2], dp[4 * i + 3], static_cast<int32_t>(j),
+                                      static_cast<int32_t>(L)) >= lb;
     int lo = nchunk, hi = -1;
     for (uint32_t k = G.pred_off[i]; k < G.pred_off[i + 1]; ++k) {
       const uint32_t p = G.preds[k];
@@ -243,6 +265,7 @@ static bool emu_align_dyn(Emu* E, const uint8_t* read, uint32_t L, int32_t lb, i
         rel = static_cast<int64_t>(hmax) + ub >= lb;
       }
       if (rel) { rlo[i] = std::min(rlo[i], t); rhi[i] = std::max(rhi[i], t); }
+      if (rel && lookahead && t == hi && hi < nchunk - 1) E->overflow = true;
       E->kept_cells += C;
     }
     E->all_cells += L;
@@ -268,6 +291,9 @@ void* emu_new(int ring_rows) {
   return e;
 }
 void emu_set_prune(void* h, int half_width) { static_cast<Emu*>(h)->prune = half_width; }
+void emu_set_dyn_ext(void* h, int chunks) { static_cast<Emu*>(h)->dyn_ext = chunks; }
+double emu_static_fraction(void* h) { Emu* e = static_cast<Emu*>(h); return e->all_cells > 0 ? e->static_cells / e->all_cells : 1.0; }
+int emu_overflows(void* h) { return static_cast<Emu*>(h)->overflows; }
 void emu_set_dyn(void* h, double lb_ratio) { static_cast<Emu*>(h)->dyn = 1; static_cast<Emu*>(h)->lb_ratio = lb_ratio; }
 int emu_retries(void* h) { return static_cast<Emu*>(h)->retries; }
 double emu_kept_fraction(void* h) { Emu* e = static_cast<Emu*>(h); return e->all_cells > 0 ? e->kept_cells / e->all_cells : 1.0; }

@@ -75,6 +75,34 @@ def test_pruned_emulation_equals_oracle(oracle):
     e.close()
 
 
+def test_lookahead_pruning_emulation_equals_oracle(oracle):
+    """Round-2 candidate, exactness on CPU: prefix-exact pruning ("H + suffix bound >= LB") where a
+    row is computed over its predecessors' relevant columns plus a FIXED lookahead of chunks; a
+    row whose last computed chunk is still relevant repeats the alignment with more lookahead.
+    Alignments stay identical for every lookahead, including 0 (always overflowing)."""
+    from tests.emul.emul import EmuSession
+    rng = np.random.default_rng(41)
+    for it in range(60):
+        seqs = _random_group(rng, it)
+        if it % 6 == 0:
+            seqs[-1] = synth._to_str(synth._rand_seq(rng, int(rng.integers(1, 90))))
+        o = oracle.PoaSession(1)
+        e = EmuSession(ring_rows=3, dyn=float(rng.choice([2.0, 4.2, 4.6, 5.0])), dyn_ext=int(rng.choice([0, 1, 2, 5])))
+        for s in seqs:
+            assert np.array_equal(o.add(s), e.add(s))
+        assert o.msa() == e.msa() and o.consensus() == e.consensus()
+        o.close()
+        e.close()
+    w = synth.make_small_window(7, body_len=1500, sv_len=40, n_tumor=5, n_normal=5, n_carriers=3)
+    e, o = EmuSession(ring_rows=12, dyn=4.4, dyn_ext=1), oracle.PoaSession(1)
+    for s in w[0]:
+        assert np.array_equal(o.add(s), e.add(s))
+    from tests.emul.emul import lib
+    assert e.kept_fraction() < lib().emu_static_fraction(e.h)    # fewer cells than the static bands
+    o.close()
+    e.close()
+
+
 def test_margin_columns_equals_reference_loop(oracle):
     rng = np.random.default_rng(0)
     for _ in range(2000):
