@@ -25,7 +25,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import numpy as np
 

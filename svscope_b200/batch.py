@@ -16,7 +16,6 @@ Windows are rows ``[sequenceList, ReadIDs, flank_5, flank_3, TDRecord]`` (the np
 """
 from __future__ import annotations
 
-import ctypes
 import time
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence

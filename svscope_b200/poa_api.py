@@ -2,11 +2,10 @@
 from __future__ import annotations
 
 import ctypes
-from typing import List, Sequence, Tuple
+from typing import List, Sequence
 
 import numpy as np
 
-from . import _lib
 from ._lib import Context, ReadSet, c_vp, load, ptr
 
 STAT_NAMES = ["cells", "alignments", "dp_ms", "tb_ms", "wall_ms", "dp_launches", "tb_launches",

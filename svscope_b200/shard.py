@@ -7,7 +7,6 @@ from __future__ import annotations
 
 from typing import List, Sequence
 
-import numpy as np
 
 
 def lpt_shards(costs: Sequence[float], n_shards: int) -> List[List[int]]:

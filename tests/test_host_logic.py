@@ -1,7 +1,6 @@
 """Host-side logic of the product on CPU: rank-order graph + cell arithmetic (through the
 sequential emulation of the kernels), flank columns, sharding, world_size-2 gather (gloo)."""
 import os
-import sys
 
 import numpy as np
 import pytest

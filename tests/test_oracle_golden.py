@@ -1,7 +1,6 @@
 """The CPU oracle against the vectors produced by the reference's own Python
 (oracle/gen_golden.py; reference files src/ReadsCluster.py, src/DataScanner.py,
 src/DecisionMaker.py).  CPU only."""
-import glob
 import json
 import os
 
