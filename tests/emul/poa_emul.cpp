@@ -202,6 +202,8 @@ static bool emu_align_dyn(Emu* E, const uint8_t* read, uint32_t L, int32_t lb, i
   const bool lookahead = have_lb && E->dyn_ext >= 0;
   int32_t best = INT32_MIN; uint32_t best_row = 0;
   const int32_t* dp = G.depth.data();
+  std::vector<uint8_t> rel0(R + 1, 0);   // column-0 cell of the row is relevant
+  rel0[0] = 1;
   for (uint32_t i = 1; i <= R; ++i) {
     P[i * W] = pack_cell(G.h0[i], kNeg, kNeg);
     if (have_lb)
@@ -212,7 +214,11 @@ static bool emu_align_dyn(Emu* E, const uint8_t* read, uint32_t L, int32_t lb, i
     for (uint32_t k = G.pred_off[i]; k < G.pred_off[i + 1]; ++k) {
       const uint32_t p = G.preds[k];
       if (rlo[p] <= rhi[p]) { lo = std::min(lo, rlo[p]); hi = std::max(hi, rhi[p] + 1); }
+      // column 0 of the predecessor (leading graph nodes skipped) is not part of any chunk: when it
+      // can still lie on a path scoring >= lb, the first chunk of this row has to be computed
+      if (rel0[p]) { lo = 0; hi = std::max(hi, 0); }
     }
+    rel0[i] = !have_lb || static_cast<int64_t>(G.h0[i]) + side_bound(s, dp[4 * i + 2], dp[4 * i + 3], static_cast<int32_t>(L)) >= lb;
     if (!have_lb) { lo = 0; hi = nchunk - 1; }
     else if (lo <= hi) hi = std::min(nchunk - 1, hi + ext);
     clo[i] = lo; chi[i] = hi;

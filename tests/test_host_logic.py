@@ -92,6 +92,16 @@ def test_lookahead_pruning_emulation_equals_oracle(oracle):
         assert o.msa() == e.msa() and o.consensus() == e.consensus()
         o.close()
         e.close()
+    # found by tests/tools/fuzz_emul.py: the co-optimal path runs through column 0 of a row whose other
+    # cells are all irrelevant (leading graph nodes skipped) - column 0 counts for the next row's range
+    for seqs, kw in ((['GA', 'AC', 'A', 'AC', 'A'], dict(dyn=1.0)),
+                     (['CG', 'AA', 'CG', 'T', 'T', 'G'], dict(dyn=5.0)),
+                     (['GA', 'C', 'A', 'CGGGAACGCTTATGAAAGA', 'GA', 'C', 'GA', 'C', 'C'], dict(dyn=5.0, dyn_ext=1))):
+        o, e = oracle.PoaSession(1), EmuSession(ring_rows=3, **kw)
+        for s in seqs:
+            assert np.array_equal(o.add(s), e.add(s))
+        o.close()
+        e.close()
     w = synth.make_small_window(7, body_len=1500, sv_len=40, n_tumor=5, n_normal=5, n_carriers=3)
     e, o = EmuSession(ring_rows=12, dyn=4.4, dyn_ext=1), oracle.PoaSession(1)
     for s in w[0]:
