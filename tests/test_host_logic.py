@@ -311,3 +311,23 @@ def test_callsomaticsv_writes_somatic_bed(tmp_path, monkeypatch, oracle):
         w = want[g[3]]
         assert g[:3] == [str(w[0]), str(w[1]), str(w[2])] and g[4:6] == [w[4], w[5]]
         assert int(g[6]) == w[6] and g[7] == w[7] and int(g[8]) == abs(w[6])
+
+
+def test_tdscope_rescue_control_flow_matches_reference(oracle):
+    """``SomTDDetector.TDscope`` (extraction callables + decision + DUP rescue, reference
+    src/SomTDDetector.py:26-61) against records the reference's own TDscope produced for the same
+    scenarios (oracle/gen_golden_tdscope.py); the decision callable is the oracle on both sides, so
+    this pins the control flow: which extraction wins, which flag is written."""
+    import json
+    from oracle.gen_golden_tdscope import makers, scenarios
+    from svscope_b200.SomTDDetector import TDscope
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tdscope_cases.json")))["records"]
+    flags = set()
+    for name in scenarios():
+        TDRecord, dm, dm2 = makers(name)
+        np.random.seed(2023)
+        rec = TDscope(TDRecord, dm, dm2, oracle.decision)
+        assert [str(x) for x in rec] == gold[name], name
+        flags.add(rec[-1])
+    assert flags == {"NormalOutput|EMOutput", "NormalOutput", "UnspanedSV|EMOutput", "UnspannedSV|EMOutput",
+                     "UnspanedSV", "UnspannedSV"}
