@@ -18,7 +18,8 @@ Pinning status
   ``decision``): **pinned** against the reference's own Python (`src/DataScanner.py`,
   `src/ReadsCluster.py`, `src/DecisionMaker.py`) imported unmodified in the build container by
   ``oracle/gen_golden.py``; the outputs are committed under ``tests/golden/`` and re-checked
-  by ``tests/test_oracle_golden.py`` wherever the suite runs.
+  by ``tests/test_oracle_golden.py`` wherever the suite runs; ``oracle/fuzz_vs_reference.py``
+  additionally compared 32 549 random windows record by record with the reference's ``Decision``.
 """
 from __future__ import annotations
 
