@@ -331,3 +331,80 @@ def test_tdscope_rescue_control_flow_matches_reference(oracle):
         flags.add(rec[-1])
     assert flags == {"NormalOutput|EMOutput", "NormalOutput", "UnspanedSV|EMOutput", "UnspannedSV|EMOutput",
                      "UnspanedSV", "UnspannedSV"}
+
+
+def _fake_em_batch(oracle):
+    """A numpy stand-in for svs_em_batch that follows the device contract of
+    include/svscope_b200.h (schedule [M from labels] E, n_steps x (M, E); status = index of the
+    M-step that met pi*N < 1 or NaN, nothing drawn on the 'device')."""
+    def m_nodraw(gamma, X):
+        N, nf = X.shape
+        pi = gamma.sum(axis=0) / N
+        if (pi * N < 1).any() or np.isnan(pi).any():
+            return None, None
+        tot = np.dot(gamma.T, np.ones((N, nf), dtype=np.int64))
+        theta = np.dstack([np.dot(gamma.T, np.where(X == a, 1, 0)) / tot for a in range(5)])
+        return pi, theta
+
+    def run(ctx, Xs, tasks, want_theta=False):
+        out = []
+        for t in tasks:
+            X = Xs[t.x_index]
+            N, K = X.shape[0], t.K
+            status, pi, theta, gamma = -1, t.pi, t.theta, None
+            if t.labels is not None:
+                g0 = np.zeros((N, K))
+                g0[np.arange(N), np.asarray(t.labels)] = 1
+                pi, theta = m_nodraw(g0, X)
+                if pi is None:
+                    status = 0
+            if status < 0:
+                gamma, _ = oracle.e_step(K, np.asarray(pi, float), np.asarray(theta, float), X)
+                for it in range(1, t.n_steps + 1):
+                    p2, t2 = m_nodraw(gamma, X)
+                    if p2 is None:
+                        status = it
+                        break
+                    pi, theta = p2, t2
+                    gamma, _ = oracle.e_step(K, pi, theta, X)
+            if status >= 0:
+                out.append(dict(gamma=np.zeros((N, K)), pi=np.zeros(K), lik=np.zeros(N), theta=None, status=status))
+            else:
+                out.append(dict(gamma=gamma, pi=np.asarray(pi, float), status=-1,
+                                lik=oracle.per_read_loglik(np.asarray(pi, float), np.asarray(theta, float), gamma, X),
+                                theta=np.asarray(theta, float) if want_theta else None))
+        return out
+    return run
+
+
+def test_em_host_driver_replays_the_reference_rng_order(oracle, monkeypatch):
+    """batch.em_cluster_many (Ward start per K, device fits, host-side Dirichlet re-draws from the
+    global RNG in the reference's order, NaN-BIC retries, K choice) with a numpy stand-in for the
+    device call: equal to oracle.em_cluster - itself fuzzed against the reference's EMCluster - on
+    random matrices, most of them small enough to hit the re-draw path."""
+    import warnings
+    monkeypatch.setattr(batch, "em_batch", _fake_em_batch(oracle))
+    rng = np.random.default_rng(5)
+    redraw = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for it in range(150):
+            N, nf = int(rng.integers(3, 22)), int(rng.integers(10, 60))
+            X = np.tile(rng.integers(0, 4, nf), (N, 1))
+            for _ in range(int(rng.integers(0, 3))):
+                rows = rng.choice(N, size=int(rng.integers(1, max(2, N // 2))), replace=False)
+                cols = rng.choice(nf, size=int(rng.integers(1, nf)), replace=False)
+                X[np.ix_(rows, cols)] = rng.integers(0, 5)
+            noise = rng.random((N, nf)) < float(rng.choice([0.0, 0.05, 0.3]))
+            X[noise] = rng.integers(0, 5, int(noise.sum()))
+            X = X.astype(np.int64)
+            want, info = oracle.em_cluster(X, reseed=True, return_info=True)
+            got = batch.em_cluster_many(None, [X], [oracle.pairwise_identity(X)], [oracle.zero_param_num(X)],
+                                        want_theta=True, reseed=True)[0]
+            assert got["K"] == want[0] and np.array_equal(got["labels"], want[2]), it
+            assert np.allclose(got["bics"], want[6], rtol=1e-9, equal_nan=True)
+            assert np.allclose(got["gamma"], want[4], rtol=1e-9, atol=1e-300) and np.allclose(got["pi"], want[5], rtol=1e-9)
+            assert np.allclose(got["theta"], want[3], rtol=1e-9, atol=1e-300)
+            assert (got["n_redraws"] > 0) == (info["n_fallback"] > 0)
+            redraw += got["n_redraws"] > 0
+    assert redraw > 30
