@@ -408,3 +408,82 @@ def test_em_host_driver_replays_the_reference_rng_order(oracle, monkeypatch):
             assert (got["n_redraws"] > 0) == (info["n_fallback"] > 0)
             redraw += got["n_redraws"] > 0
     assert redraw > 30
+
+
+def _device_stand_ins(oracle, monkeypatch):
+    """Replace every device wrapper used by batch.localgraph_batch with an oracle/numpy stand-in
+    that follows the same contract (the GPU suite tests the real ones against the oracle)."""
+    import types
+    from svscope_b200 import poa_api
+
+    def fake_upload(ctx, windows):
+        seqs = [s for w in windows for s in w[0]] + [""]
+        off = np.zeros(len(seqs) + 1, np.int64)
+        off[1:] = np.cumsum([len(s) for s in seqs])
+        return types.SimpleNamespace(seqs=seqs, off=off, nbytes=int(off[-1]))
+
+    def fake_poa_groups(ctx, reads, groups, algorithm=1, want_msa=True, scores=None, as_array=False):
+        cons, msas = [], []
+        for g in groups:
+            c, m = oracle.poa([reads.seqs[i] for i in g], algorithm) if len(g) else ("", [])
+            cons.append(c)
+            if want_msa and as_array:
+                msas.append(np.frombuffer("".join(m).encode(), np.uint8).reshape(len(m), -1) if m else np.zeros((0, 0), np.uint8))
+            else:
+                msas.append(m if want_msa else [])
+        return cons, msas, {k: 0.0 for k in poa_api.STAT_NAMES}
+
+    def fake_msa_features(ctx, encs, drops, cutoffs):
+        out = []
+        for e, d, cut in zip(encs, drops, cutoffs):
+            e = np.asarray(e).astype(np.int64)
+            cols = np.flatnonzero(np.asarray(d) == 0)
+            sub = e[:, cols]
+            keep = np.zeros(e.shape[1], bool)
+            keep[cols[oracle.find_non_same_site(sub, cutoff=cut)]] = True
+            X = e[:, keep]
+            ident = (X[:, None, :] == X[None, :, :]).sum(axis=2).astype(np.int32)
+            out.append((keep, int(keep.sum()), oracle.zero_param_num(X) if X.size else 0, ident))
+        return out
+
+    monkeypatch.setattr(batch, "upload_windows", fake_upload)
+    monkeypatch.setattr(batch, "poa_groups", fake_poa_groups)
+    monkeypatch.setattr(batch, "msa_features", fake_msa_features)
+    monkeypatch.setattr(batch, "em_batch", _fake_em_batch(oracle))
+
+
+def test_batch_host_orchestration_equals_oracle_with_device_stand_ins(oracle, monkeypatch):
+    """Everything batch.localgraph_batch does on the host - gates, the empty-read quirk, flank
+    columns, feature cut-off, EM driver with per-window reseeding, cluster labelling, consensus
+    grouping ('-' for empty clusters), record assembly, batching of several windows - against
+    oracle.decision (itself fuzzed against the reference's Decision) on random windows with
+    empty reads, a third tag and non-default cut-offs."""
+    import warnings
+    _device_stand_ins(oracle, monkeypatch)
+    rng = np.random.default_rng(17)
+    n_em = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for b in range(10):
+            wins = []
+            for _ in range(6):
+                nt, nn = int(rng.integers(2, 10)), int(rng.integers(2, 10))
+                w = synth.make_sv_window(int(rng.integers(1 << 30)), int(rng.integers(120, 320)),
+                                         "DEL" if rng.random() < 0.5 else "INS", int(rng.integers(10, 90)), nt, nn,
+                                         int(rng.integers(0, nt + 1)), float(rng.choice([0.0, 0.03, 0.1])))
+                seqs, ids = list(w[0]), np.array(w[1])
+                r = rng.random()
+                if r < 0.2:
+                    for k in rng.choice(np.arange(1, len(seqs)), size=int(rng.integers(1, 3)), replace=False):
+                        seqs[int(k)] = ""
+                elif r < 0.3:
+                    ids = np.array([x.replace("_normal|", "_other|") if rng.random() < 0.4 else x for x in ids])
+                wins.append([seqs, ids, w[2], w[3], w[4]])
+            kw = dict(readcutoff=int(rng.integers(2, 5)), hcutoff=int(rng.integers(2, 5)),
+                      scutoff=float(rng.choice([0.05, 0.2]))) if b % 3 == 2 else {}
+            got = batch.localgraph_batch(wins, ctx=object(), **kw).records
+            for w, g in zip(wins, got):
+                want = oracle.decision(w[4], w[0], w[1], w[2], w[3], **kw)
+                assert [str(x) for x in want] == [str(x) for x in g]
+                n_em += str(g[-1]).endswith("EMOutput")
+    assert n_em >= 10
