@@ -12,8 +12,10 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(HERE, "poa_emul.cpp"), os.path.join(ROOT, "svscope_b200", "csrc", "poa_graph.cpp")]
-    deps = srcs + [os.path.join(ROOT, "svscope_b200", "csrc", h) for h in ("poa_cell.h", "poa_graph.h")]
+    srcs = [os.path.join(HERE, "poa_emul.cpp"), os.path.join(HERE, "dgraph_emul.cpp"),
+            os.path.join(ROOT, "svscope_b200", "csrc", "poa_graph.cpp")]
+    deps = srcs + [os.path.join(ROOT, "svscope_b200", "csrc", h)
+                   for h in ("poa_cell.h", "poa_graph.h", "poa_dgraph.h", "poa_task.h")]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w"] + srcs + ["-o", LIB], check=True)
@@ -49,8 +51,22 @@ def lib():
         L.emu_retries.argtypes = [ctypes.c_void_p]
         L.emu_kept_fraction.restype = ctypes.c_double
         L.emu_kept_fraction.argtypes = [ctypes.c_void_p]
+        L.dgraph_emul_check.restype = ctypes.c_int
+        L.dgraph_emul_check.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
         _lib = L
     return _lib
+
+
+def dgraph_check(seqs, ring_rows=4, n_threads=128):
+    """Runs the device-resident graph code (poa_dgraph.h) on the CPU over the sequence group and
+    compares every array with the host graph after every read.  Returns '' or the first difference."""
+    enc = [s.encode() for s in seqs]
+    off = np.zeros(len(enc) + 1, np.int64)
+    off[1:] = np.cumsum([len(b) for b in enc])
+    msg = ctypes.create_string_buffer(512)
+    rc = lib().dgraph_emul_check(b"".join(enc), off.ctypes.data, len(enc), ring_rows, n_threads, 0, msg, 512)
+    return "" if rc == 0 else (msg.value.decode() or "mismatch")
 
 
 class EmuSession:
