@@ -38,13 +38,11 @@ int svs_create(int device, svs_ctx** out);
 void svs_destroy(svs_ctx* ctx);
 const char* svs_last_error(const svs_ctx* ctx);
 const char* svs_version(void);
-/* Options (all optional): "poa_threads" CTA size of the alignment kernel (128|256|512; default
- * 256), "poa_cols" read columns per thread (4|8|16; default 8), "ring_rows" packed rows kept in
- * shared memory (default 12), "prune" exact score-bound pruning (default 1), "streams" concurrent
- * round streams (default 2), "workers" host threads for graph merge/export (default 4),
- * "arena_mb" device scratch arena in MiB (0 = 85 % of free memory).  The persistent kernel
- * (per-SM scratch slots, fused traceback, pruning) runs for 256x8 (two CTAs per SM), 512x8,
- * 512x4 and 256x16; other shapes take the classic one-CTA-per-alignment launch. */
+/* Options (all optional): "poa_threads" CTA size of the window kernel (128|256|512; default
+ * 128), "poa_cols" read columns per thread (4 with 512 threads | 8 | 16 with 256 threads; default
+ * 8), "ring_rows" packed rows kept in shared memory (default 10), "prune" exact score-bound
+ * pruning (default 1), "arena_mb" device scratch arena in MiB (0 = 85 % of free memory).
+ * Resident windows per SM: 4 for 128x8, 2 for 256x8, 1 for 256x16 / 512x8 / 512x4. */
 int svs_set_option(svs_ctx* ctx, const char* key, int64_t value);
 int64_t svs_get_option(const svs_ctx* ctx, const char* key);
 
@@ -70,20 +68,32 @@ void svs_reads_free(svs_reads* reads);
 int svs_poa_batch(svs_ctx* ctx, const svs_reads* reads, const int64_t* members,
                   const int64_t* group_off, int64_t n_groups, int algorithm, int m, int n, int g,
                   int e, int q, int c, int want_msa, svs_poa_result** out);
+/* The same in two halves: submit enqueues the window kernel on its own stream and returns at
+ * once (other calls on the context may run meanwhile and overlap with it on the device);
+ * wait blocks until the groups are done (and repeats, in a larger memory tier, the groups
+ * whose graph or traceback did not fit their scratch slot). */
+int svs_poa_submit(svs_ctx* ctx, const svs_reads* reads, const int64_t* members,
+                   const int64_t* group_off, int64_t n_groups, int algorithm, int m, int n, int g,
+                   int e, int q, int c, int want_msa, svs_poa_result** out);
+int svs_poa_wait(svs_poa_result* res);
+/* per group: 0 = done; > 0 = the group could not be aligned (1-5, 8: does not fit the largest
+ * memory tier; 3: aligned group of more than 8 letters; 7: |V| + L beyond the score format;
+ * 10: a node with more than 31 in-edges).  A failed group has empty outputs; the other groups
+ * of the call are not affected. */
+int svs_poa_result_status(const svs_poa_result* res, int32_t* status);
 /* per group: consensus length, MSA rows (non-empty sequences) and MSA columns */
 int svs_poa_result_sizes(const svs_poa_result* res, int64_t* cons_len, int64_t* msa_rows,
                          int64_t* msa_cols);
 /* consensus strings concatenated in group order; MSA matrices (rows*cols chars, row-major)
  * concatenated in group order.  Either pointer may be NULL. */
 int svs_poa_result_copy(const svs_poa_result* res, uint8_t* consensus, uint8_t* msa);
-/* stats[0] DP cells, [1] alignments, [2] sum of DP-kernel ms (events on the launch streams),
- * [3] sum of traceback-kernel ms, [4] wall ms of the call, [5] launches of the DP kernel,
- * [6] launches of the traceback kernel, [7] bytes host->device, [8] bytes device->host,
- * [9] algorithmic bytes (read + graph + path), [10] exported rows,
- * [11] graph rows total, [12..15] host ms: waiting for the device, merging paths into graphs,
- * exporting rank-ordered graphs, packing the staging buffer, [18] ms spent issuing launches,
- * [22] D2H ms on the streams, [23] pruning retries (alignments repeated because the guessed
- * score bound was too high) */
+/* stats[0] nominal DP cells sum (|V|+1)(L+1), [1] alignments, [2] ms of the window kernel
+ * (events on its stream, summed over launches), [4] wall ms submit..wait, [5] kernel launches,
+ * [7] bytes host->device, [8] bytes device->host (records; the MSA/consensus copy is counted by
+ * the caller), [9] algorithmic bytes (read + rank-ordered graph + path),
+ * [10] rows exported to global memory, [11] graph rows total, [23] pruning retries,
+ * [24..29] SM cycles of thread 0 per phase summed over windows: export, bands + DP,
+ * traceback, merge, rank order, MSA/consensus, [32] groups with a non-zero status */
 int svs_poa_result_stats(const svs_poa_result* res, double* stats, int n_stats);
 void svs_poa_result_free(svs_poa_result* res);
 

@@ -28,7 +28,10 @@ for rep in range(int(os.environ.get("REPS", 1))):
     print(" poa cells %.3e aligns %d dp_ms(sum) %.0f tb_ms(sum) %.0f launches %d h2d %.1fMB d2h %.1fMB exported_rows %.1f%%" % (
         st["poa_cells"], st["poa_alignments"], st["poa_dp_ms"], st["poa_tb_ms"], st["poa_dp_launches"],
         st["poa_h2d_bytes"] / 1e6, st["poa_d2h_bytes"] / 1e6, 100 * st["poa_exported_rows"] / max(1, st["poa_rows"])), flush=True)
-    print(" host ms (sum over workers): wait %.0f merge %.0f plan %.0f pack %.0f" % (st["poa_host_wait_ms"], st["poa_host_merge_ms"], st["poa_host_plan_ms"], st["poa_host_pack_ms"]), "refill %.0f starved_polls %.0f launch %.0f final %.0f" % (st["poa_refill_ms"], st["poa_starved_polls"], st["poa_launch_ms"], st["poa_final_ms"]), "inflight %.0f h2d %.0f d2h %.0f" % (st["poa_inflight_ms"], st["poa_h2d_ms"], st["poa_d2h_ms"]), flush=True)
+    cyc = {k: st["poa_cyc_" + k] for k in ("export", "dp", "traceback", "merge", "rank", "finish")}
+    tot = max(1.0, sum(cyc.values()))
+    print(" window-kernel phase shares (thread-0 cycles): " + ", ".join("%s %.1f%%" % (k, 100 * v / tot) for k, v in cyc.items()),
+          "| retries %d failed %d" % (st["poa_prune_retries"], st["poa_failed_windows"]), flush=True)
     poa_t = out.timings["poa_msa"] + out.timings["poa_consensus"]
     print(" POA wall GCUPS %.1f ; ED cells %.3e in %.1f ms -> %.0f GCUPS" % (
         st["poa_cells"] / poa_t / 1e9, st["ed_cells"], st["ed_ms"], st["ed_cells"] / max(st["ed_ms"], 1e-9) / 1e6), flush=True)

@@ -31,6 +31,9 @@ SYMBOLS = {
     "svs_reads_upload": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_vp)]),
     "svs_reads_free": (None, [c_vp]),
     "svs_poa_batch": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64] + [ctypes.c_int] * 8 + [ctypes.POINTER(c_vp)]),
+    "svs_poa_submit": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64] + [ctypes.c_int] * 8 + [ctypes.POINTER(c_vp)]),
+    "svs_poa_wait": (ctypes.c_int, [c_vp]),
+    "svs_poa_result_status": (ctypes.c_int, [c_vp, c_vp]),
     "svs_poa_result_sizes": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "svs_poa_result_copy": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "svs_poa_result_stats": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int]),

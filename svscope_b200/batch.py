@@ -355,7 +355,15 @@ def localgraph_batch(windows, ctx: Optional[Context] = None, reads: Optional[Rea
     # ---- stage 2: window MSA ---------------------------------------------------------------
     t1 = time.perf_counter()
     groups = [list(range(int(base[i]), int(base[i + 1]))) for i in live]
-    _, msas, st_msa = poa_groups(ctx, reads, groups, want_msa=True, as_array=True)
+    _, msas, st_msa = poa_groups(ctx, reads, groups, want_msa=True, as_array=True, strict=False)
+    if st_msa["status"].any():
+        # a window the device cannot align (graph beyond the largest memory tier, more than 31
+        # in-edges at one node, ...) fails alone: flagged record, the batch goes on
+        ok = [k for k in range(len(live)) if st_msa["status"][k] == 0]
+        for k in np.flatnonzero(st_msa["status"]):
+            records[live[k]][9] = flags[live[k]] + "|GraphLimit%d" % int(st_msa["status"][k])
+        live = [live[k] for k in ok]
+        msas = [msas[k] for k in ok]
     tm["poa_msa"] = time.perf_counter() - t1
     # ---- stage 3: encode, margins, features ---------------------------------------------------
     t1 = time.perf_counter()
@@ -422,7 +430,8 @@ def localgraph_batch(windows, ctx: Optional[Context] = None, reads: Optional[Rea
                     nonzero = any(reads.off[s + 1] - reads.off[s] > 0 for s in src)
                     cons_groups.append(src if nonzero else [])
                     cons_owner.append((k, kind, c, nonzero))
-    cons, _, st_cons = poa_groups(ctx, reads, cons_groups, want_msa=False)
+    cons, _, st_cons = poa_groups(ctx, reads, cons_groups, want_msa=False, strict=False)
+    bad_cons = {cons_owner[k][0] for k in np.flatnonzero(st_cons["status"])}
     tm["poa_consensus"] = time.perf_counter() - t1
     # ---- stage 7: records ----------------------------------------------------------------------
     t1 = time.perf_counter()
@@ -436,7 +445,9 @@ def localgraph_batch(windows, ctx: Optional[Context] = None, reads: Optional[Rea
         if keep_aux:
             aux[i] = dict(K=fit["K"], labels=fit["labels"], gamma=fit["gamma"], pi=fit["pi"], bics=fit["bics"],
                           n_redraws=fit["n_redraws"], nf=Xs[em_idx.index(k)].shape[1])
-        if len(som) > 0 and len(germ) > 0:                                  # DecisionMaker.py:178
+        if k in bad_cons:
+            records[i][9] = flags[i] + "|GraphLimit"
+        elif len(som) > 0 and len(germ) > 0:                                  # DecisionMaker.py:178
             rec = records[i]
             records[i] = [rec[0], rec[1], rec[2],
                           ";".join(seq_out[(k, "som", c)] for c in range(len(som))),
@@ -459,7 +470,8 @@ def localgraph_batch(windows, ctx: Optional[Context] = None, reads: Optional[Rea
             dists[i] = m
         tm["edit_distance"] = time.perf_counter() - t1
     tm["total"] = time.perf_counter() - t0
-    stats = {"poa_" + k: st_msa[k] + st_cons[k] for k in st_msa}
+    stats = {"poa_" + k: st_msa[k] + st_cons[k] for k in st_msa if k != "status"}
+    stats["poa_failed_windows"] = int(np.count_nonzero(st_msa["status"])) + len(bad_cons)
     stats.update({"ed_" + k: v for k, v in st_ed.items()})
     stats.update(ACCT)
     stats["windows"] = nw

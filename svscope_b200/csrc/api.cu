@@ -218,8 +218,12 @@ int svs_reads_upload(svs_ctx* ctx, const uint8_t* seqs, const int64_t* off, int6
     if (pinned) cudaHostUnregister(r->host.data());
     else cudaGetLastError();
   }
+  if (err == cudaSuccess) err = cudaMalloc(reinterpret_cast<void**>(&r->dev_off), sizeof(int64_t) * (static_cast<size_t>(n_seqs) + 1));
+  if (err == cudaSuccess)
+    err = cudaMemcpy(r->dev_off, r->off.data(), sizeof(int64_t) * (static_cast<size_t>(n_seqs) + 1), cudaMemcpyHostToDevice);
   if (err != cudaSuccess) {
     if (r->dev) cudaFree(r->dev);
+    if (r->dev_off) cudaFree(r->dev_off);
     delete r;
     return fail(ctx, SVS_ERR_CUDA, std::string("reads upload: ") + cudaGetErrorString(err));
   }
@@ -231,6 +235,7 @@ void svs_reads_free(svs_reads* reads) {
   if (!reads) return;
   if (reads->ctx) cudaSetDevice(reads->ctx->device);
   if (reads->dev) cudaFree(reads->dev);
+  if (reads->dev_off) cudaFree(reads->dev_off);
   delete reads;
 }
 

@@ -12,8 +12,8 @@ OUT_DIR = os.path.join(PKG, "_C")
 LIB = os.path.join(OUT_DIR, "libsvscope_b200.so")
 OBJ_DIR = os.path.join(HERE, "_build")
 
-CU_SOURCES = ["api.cu", "poa_kernels.cu", "poa_batch.cu", "msa_features.cu", "em.cu", "myers.cu", "misscore.cu"]
-CXX_SOURCES = ["poa_graph.cpp"]
+CU_SOURCES = ["api.cu", "poa_kernels.cu", "poa_window.cu", "msa_features.cu", "em.cu", "myers.cu", "misscore.cu"]
+CXX_SOURCES = []
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall", "--expt-relaxed-constexpr"]
 

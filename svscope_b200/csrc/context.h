@@ -14,10 +14,10 @@ struct svs_ctx {
   int device = 0;
   std::string error;
   // options
-  int poa_threads = 256;   // 256 threads x 8 columns: two resident alignments per SM
+  int poa_threads = 128;   // 128 threads x 8 columns: four resident windows per SM
   int prune = 1;       // exact score-bound pruning of DP cells (persistent kernel)
   int poa_cols = 8;    // read columns per thread (16 only with 256 threads)
-  int ring_rows = 12;
+  int ring_rows = 10;
   int workers = 4;
   int64_t arena_mb = 0;
   int lane_jobs = 0;   // alignments per round of a lane (0 = derived)
@@ -37,6 +37,7 @@ struct svs_reads {
   std::vector<uint8_t> host;     // concatenated sequences
   std::vector<int64_t> off;      // n+1
   uint8_t* dev = nullptr;        // device copy of `host`
+  int64_t* dev_off = nullptr;    // device copy of `off`
   int64_t n = 0;
 };
 

@@ -1,7 +1,7 @@
 // Partial-order graph of one window, resident in DEVICE memory, and every graph step of
 // `spoa.poa(sequences, 1)` between two alignments (reference call sites src/DataScanner.py:206,213
 // and src/DecisionMaker.py:160,171; behaviour of spoa's Graph as restated in SURVEY.md
-// Appendix B and oracle/spoa_oracle.cpp): merge of an alignment path (AddAlignment), rank
+// Appendix B): merge of an alignment path (AddAlignment), rank
 // order (TopologicalSort, depth-first over node ids), export of the rank-ordered arrays the
 // DP kernel consumes, MSA rows and heaviest-bundle consensus.
 //
@@ -37,6 +37,7 @@ enum WinStatus : int32_t {
   kWinScoreSpan = 7,    // |V| + L too large for the packed cell format
   kWinOutCap = 8,       // output arena exhausted
   kWinPending = 9,
+  kWinIndeg = 10,       // a node with more than 31 in-edges (index field of the traceback codes)
 };
 
 struct WinCaps {
@@ -66,6 +67,7 @@ struct WinMem {
   int32_t* at;           // [lmax] merge scratch: node aligned to / chosen for each read position
   int32_t* flag;         // [lmax] merge scratch
   int32_t* path_node;    // [sumlen] node of every base of every merged sequence
+  uint32_t* seq_len;     // [nseq] lengths of the merged (non-empty) sequences, in merge order
   // rank-ordered view (the arrays of PoaTask), indexed by row 0..R
   uint8_t* r_letter;
   uint8_t* r_flags;
@@ -114,6 +116,7 @@ SVS_HD uint64_t win_layout(uint8_t* base, uint64_t slot_bytes, const WinCaps& c,
   m->at = reinterpret_cast<int32_t*>(take(4 * L));
   m->flag = reinterpret_cast<int32_t*>(take(4 * L));
   m->path_node = reinterpret_cast<int32_t*>(take(4 * (c.sumlen + 8)));
+  m->seq_len = reinterpret_cast<uint32_t*>(take(4 * (static_cast<uint64_t>(c.nseq) + 8)));
   m->r_letter = take(V1);
   m->r_flags = take(V1);
   m->pred_off = reinterpret_cast<uint32_t*>(take(4 * (V1 + 1)));
@@ -176,6 +179,7 @@ SVS_HD void dg_init_chain(X& x, const WinMem& m, const WinCaps& c, WinState* S, 
   x.one([&]() {
     S->nv = L;
     S->ne = L - 1;
+    m.seq_len[0] = L;
     S->nseq = 1;
     S->path_off += L;
   });
@@ -303,6 +307,7 @@ SVS_HD void dg_add_alignment(X& x, const WinMem& m, const WinCaps& c, WinState* 
   x.one([&]() {
     S->nv += S->n_new;
     S->ne += L ? static_cast<uint32_t>(m.flag[L - 1]) : 0;
+    m.seq_len[S->nseq] = L;
     S->nseq += 1;
     S->path_off += L;
   });

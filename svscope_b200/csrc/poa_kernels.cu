@@ -28,6 +28,7 @@
 #include "poa_cell.h"
 #include "poa_kernels.h"
 #include "poa_task.h"
+#include "poa_window.h"
 
 namespace svs {
 
@@ -447,14 +448,6 @@ __device__ __forceinline__ void dp_align(const PoaTask& tk, const Scores& s, con
   }
 }
 
-template <int T, int kC>
-__global__ void __launch_bounds__(T, (kC == 16 ? 1 : 512 / T)) poa_dp_kernel(const PoaTask* __restrict__ tasks, const Scores s,
-                                                            const SingleTables tabs, const int ring_rows) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const PoaTask tk = tasks[blockIdx.x];
-  dp_align<T, kC, kFull>(tk, s, tabs, ring_rows, smem_raw, nullptr);
-}
-
 // Band of every row: the columns whose upper bound (cell_bound, concave in the column) reaches
 // the lower bound `lb` of the optimal score.
 template <int T, int kC>
@@ -467,7 +460,7 @@ __device__ void compute_bands(const PoaTask& tk, const Scores& s, int32_t lb, bo
   for (uint32_t i = 1 + threadIdx.x; i <= tk.R; i += T) {
     int32_t lo = 1, hi = L;
     if (have_lb) {
-      const int4 d = __ldg(reinterpret_cast<const int4*>(tk.depth) + i);
+      const int4 d = *(reinterpret_cast<const int4*>(tk.depth) + i);   // written by this CTA (device-resident graph): no read-only path
       auto ub = [&](int32_t j) { return cell_bound(s, d.x, d.y, d.z, d.w, j, L); };
       // maximiser: one of the breakpoints of the two concave pieces
       int32_t cand[6] = {1, L, d.x, d.y, L - d.w, L - d.z};
@@ -561,93 +554,258 @@ __device__ void tb_walk_warp(const PoaTask& tk, const Scores& s, const int32_t* 
   if (lane == 0) tk.result[2] = ok ? n : -1;
 }
 
-// Persistent variant: one CTA per SM pulls alignments (sorted largest first) from a device
-// counter, keeps its traceback codes / exported rows / strip boundaries in the scratch slot
-// of its SM (slot = %smid: with > 114 KB of shared memory only one such CTA fits an SM), and
-// walks the traceback itself as soon as the dynamic programme of the alignment is done.
-template <int T, int kC>
-__global__ void __launch_bounds__(T, (T == 256 && kC == 8) ? 2 : 1)
-poa_persistent_kernel(const PoaTask* __restrict__ tasks, const int n_tasks, int* __restrict__ counter, uint8_t* slot_base,
-                      const uint64_t slot_bytes, int* __restrict__ slot_flags, const int slots_per_sm, const Scores s,
-                      const SingleTables tabs, const int ring_rows) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_next;
-  __shared__ int s_slot;
-  unsigned smid;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-  // scratch slot: one per SM, or (two resident CTAs per SM) one of the SM's slots taken with a flag
-  if (threadIdx.x == 0) {
-    int k = 0;
-    if (slots_per_sm > 1) {
-      while (atomicCAS(&slot_flags[smid * slots_per_sm + k], 0, 1) != 0) k = (k + 1 == slots_per_sm) ? 0 : k + 1;
+// ---------------------------------------------------------------------------------------------
+// Window kernel: the CTA owns a window (group of sequences) from its first to its last read.
+// Per read: rank-ordered export of the graph (poa_dgraph.h) -> bands -> dynamic programme ->
+// traceback -> merge of the path into the graph -> rank order; at the end MSA rows and the
+// heaviest-bundle consensus are written to the output arena.  The graph never leaves the
+// device; the host only sees the result record of the window.
+struct CtaExec {
+  uint32_t* warp_tot;   // shared memory, 32 words
+  template <class F> __device__ __forceinline__ void run(F f) { f(threadIdx.x, blockDim.x); __syncthreads(); }
+  template <class F> __device__ __forceinline__ void one(F f) { if (threadIdx.x == 0) f(); __syncthreads(); }
+  template <class F, class G> __device__ __forceinline__ void two(F f, G g) {
+    if (threadIdx.x == 0) f(); else if (threadIdx.x == 32) g();
+    __syncthreads();
+  }
+  __device__ __forceinline__ void atomic_max(uint32_t* p, uint32_t v) { atomicMax(p, v); }
+  __device__ void scan(uint32_t* a, uint32_t n) {
+    const uint32_t nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n; base += nt) {
+      const uint32_t i = base + tid;
+      uint32_t v = i < n ? a[i] : 0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= static_cast<uint32_t>(d)) v += o;
+      }
+      if (lane == 31) warp_tot[warp] = v;
+      __syncthreads();
+      uint32_t add = carry, total = 0;
+      for (uint32_t w = 0; w < nw; ++w) {
+        const uint32_t t = warp_tot[w];
+        if (w < warp) add += t;
+        total += t;
+      }
+      if (i < n) a[i] = v + add;
+      carry += total;
+      __syncthreads();
     }
-    s_slot = static_cast<int>(smid) * slots_per_sm + k;
+  }
+};
+
+template <int T, int kC>
+__global__ void __launch_bounds__(T, (T == 128 ? 4 : (T == 256 && kC == 8 ? 2 : 1)))
+poa_window_kernel(const WinParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ WinState S;
+  __shared__ WinMem m;
+  __shared__ PoaTask tk;
+  __shared__ WinCaps caps;
+  __shared__ uint32_t warp_tot[32];
+  __shared__ unsigned long long cyc[8];
+  __shared__ int s_next, s_slot;
+  __shared__ uint64_t s_cells, s_rows, s_exported, s_need, s_pairs, s_bases, s_steps, s_preds;
+  __shared__ uint32_t s_nalign, s_retries;
+  CtaExec x{warp_tot};
+  const int tid = threadIdx.x;
+  // scratch slot: any free one (at most n_slots CTAs of this kernel are resident at a time)
+  if (tid == 0) {
+    int k = static_cast<int>((blockIdx.x * 7919u) % static_cast<unsigned>(P.n_slots));
+    while (atomicCAS(&P.slot_flags[k], 0, 1) != 0) k = (k + 1 == P.n_slots) ? 0 : k + 1;
+    s_slot = k;
   }
   __syncthreads();
-  const int my_slot = s_slot;
-  uint8_t* slot = slot_base + static_cast<uint64_t>(my_slot) * slot_bytes;
+  uint8_t* const slot = P.slot_base + static_cast<uint64_t>(s_slot) * P.slot_bytes;
+  const Scores s = P.s;
   while (true) {
     __syncthreads();
-    if (threadIdx.x == 0) s_next = atomicAdd(counter, 1);
+    if (tid == 0) s_next = atomicAdd(P.counter, 1);
     __syncthreads();
-    const int idx = s_next;
-    if (idx >= n_tasks) break;
-    PoaTask tk = tasks[idx];
-    tk.codes = slot + tk.off_codes;
-    tk.xrows = reinterpret_cast<int32_t*>(slot + tk.off_xrows);
-    tk.bnd = reinterpret_cast<int32_t*>(slot + tk.off_bnd);
-    // Exact pruning with a guessed lower bound: bands from the bound "cell_bound >= lb" are valid
-    // whenever lb <= optimal score.  The host guesses lb from the previous alignment of the same
-    // graph; a result below the guess proves the guess was too high, and the pass is repeated
-    // with the score just found (feasible, hence a true lower bound) or without pruning.
-    int32_t* band = nullptr;
-    if (threadIdx.x == 0) tk.result[3] = 0;
-    if (tk.prune) {
-      band = reinterpret_cast<int32_t*>(slot + tk.off_band);
-      int32_t lb = tk.lb_guess;
-      bool have_lb = true;
-      bool overflow = false;
-      for (int attempt = 0; attempt < 3; ++attempt) {
-        if (threadIdx.x == 0) { tk.result[0] = 0; tk.result[1] = INT32_MIN; }
-        compute_bands<T, kC>(tk, s, lb, have_lb, band);
-        {   // do the band-limited code rows fit the slot?
-          const uint64_t n1 = tk.single_before[tk.R + 1];
-          const uint64_t need = n1 * static_cast<uint32_t>(band[0]) + (static_cast<uint64_t>(tk.R) - n1) * static_cast<uint32_t>(band[1]) + 64;
-          if (need > tk.codes_cap) { overflow = true; break; }
-        }
-        dp_align<T, kC, kFull>(tk, s, tabs, ring_rows, smem_raw, band);
-        const int32_t found_row = tk.result[0], found = tk.result[1];
-        if (!have_lb || (found_row > 0 && found >= lb)) break;   // consistent with the bound used
-        if (threadIdx.x == 0) atomicAdd(reinterpret_cast<int*>(tk.result + 3), 1);   // count the retry
-        have_lb = found_row > 0 && found > kNegBand / 2;
-        lb = found;
-        __syncthreads();
-      }
-      if (overflow) {   // the host repeats this alignment with an explicit full-size block
-        if (threadIdx.x == 0) { tk.result[0] = -2; tk.result[2] = 0; }
+    if (s_next >= P.n_windows) break;
+    const int widx = P.order[s_next];
+    const WinDesc d = P.desc[widx];
+    if (tid == 0) {
+      caps = d.caps;
+      const uint64_t fixed = win_layout(slot, P.slot_bytes, d.caps, &m);
+      S.nv = S.ne = S.nseq = 0;
+      S.path_off = 0;
+      S.err = fixed + 4096 > P.slot_bytes ? kWinNodeCap : kWinOk;
+      S.max_indeg = 1; S.n_export = S.n_single = S.n_new = S.msa_cols = 0;
+      S.last_score = 0; S.last_len = 0;
+      for (int k = 0; k < 8; ++k) cyc[k] = 0;
+      s_cells = s_rows = s_exported = s_need = s_pairs = s_bases = s_steps = s_preds = 0;
+      s_nalign = s_retries = 0;
+    }
+    __syncthreads();
+    for (uint32_t q = 0; q < d.caps.nseq && S.err == kWinOk; ++q) {
+      const int64_t id = P.members[d.member_begin + q];
+      const int64_t o0 = P.read_off[id];
+      const uint32_t L = static_cast<uint32_t>(P.read_off[id + 1] - o0);
+      const uint8_t* seq = P.reads + o0;
+      if (P.pair_cnt != nullptr && tid == 0) P.pair_cnt[d.member_begin + q] = 0;
+      if (L == 0) continue;                       // empty sequences are ignored (no MSA row)
+      if (S.nseq == 0) {
+        dg_init_chain(x, m, caps, &S, seq, L);
         continue;
       }
-    } else {
-      dp_align<T, kC, kFull>(tk, s, tabs, ring_rows, smem_raw, nullptr);
+      long long t0 = clock64();
+      dg_export(x, m, caps, &S, s, static_cast<uint32_t>(P.ring_rows), false);
+      if (tid == 0) {
+        const long long t1 = clock64();
+        cyc[0] += static_cast<unsigned long long>(t1 - t0);
+        const uint32_t R = S.nv;
+        tk.letter = m.r_letter; tk.pred_off = m.pred_off; tk.preds = m.preds; tk.flags = m.r_flags;
+        tk.xslot = m.xslot; tk.h0 = m.h0; tk.col0code = m.col0code; tk.node_id = m.node_id;
+        tk.single_before = m.single_before; tk.depth = m.depth; tk.read = seq;
+        tk.R = R; tk.L = L;
+        const uint32_t cpp = T * kC;
+        tk.npass = (L + cpp - 1) / cpp;
+        tk.strip = ((L + tk.npass - 1) / tk.npass + kC - 1) / kC * kC;
+        tk.w1 = static_cast<uint32_t>((static_cast<uint64_t>(L) + kC - 1 + 15) / 16 * 16);
+        tk.w2 = static_cast<uint32_t>((static_cast<uint64_t>(L) + kC - 1 + 7) / 8 * 8 * 2);
+        tk.ldx = (static_cast<uint64_t>(L) + 3 + kC + 7) / 8 * 8;
+        const uint64_t xbytes = dg_align(static_cast<uint64_t>(S.n_export) * tk.ldx * 4, 256);
+        tk.xrows = reinterpret_cast<int32_t*>(m.dyn);
+        tk.codes = m.dyn + xbytes;
+        tk.codes_cap = m.dyn_bytes > xbytes ? m.dyn_bytes - xbytes : 0;
+        tk.bnd = m.bnd; tk.result = m.result; tk.path = m.path; tk.path_cap = m.path_cap;
+        const int64_t span = 10ll * (static_cast<int64_t>(R) + L + 2);
+        tk.prune = (P.prune && L >= 1024 && R >= 1024 && span < (1 << 21)) ? 1u : 0u;
+        const double spb = S.last_len ? static_cast<double>(S.last_score) / S.last_len : 4.0;
+        tk.lb_guess = static_cast<int32_t>((spb - P.prune_margin) * static_cast<double>(L)) - 40;
+        const uint64_t n1 = S.n_single;
+        const uint64_t full = n1 * tk.w1 + (static_cast<uint64_t>(R) - n1) * tk.w2 + 64;
+        if (S.max_indeg > kMaxIndeg) S.err = kWinIndeg;
+        else if (span >= kMaxKeySpan) S.err = kWinScoreSpan;
+        else if (xbytes + 4096 > m.dyn_bytes || (!tk.prune && full > tk.codes_cap)) { S.err = kWinCodesCap; s_need = full + xbytes; }
+        s_cells += (static_cast<uint64_t>(R) + 1) * (static_cast<uint64_t>(L) + 1);
+        s_rows += R;
+        s_exported += S.n_export;
+        s_bases += L;
+        s_preds += m.pred_off[R + 1];
+        s_nalign += 1;
+        m.result[3] = 0;
+      }
+      __syncthreads();
+      if (S.err != kWinOk) break;
+      t0 = clock64();
+      int32_t* band = nullptr;
+      if (tk.prune) {
+        // exact pruning with a guessed lower bound (see poa_persistent_kernel)
+        band = m.band;
+        int32_t lb = tk.lb_guess;
+        bool have_lb = true, overflow = false;
+        for (int attempt = 0; attempt < 3; ++attempt) {
+          if (tid == 0) { tk.result[0] = 0; tk.result[1] = INT32_MIN; }
+          compute_bands<T, kC>(tk, s, lb, have_lb, band);
+          {
+            const uint64_t n1 = tk.single_before[tk.R + 1];
+            const uint64_t need = n1 * static_cast<uint32_t>(band[0]) + (static_cast<uint64_t>(tk.R) - n1) * static_cast<uint32_t>(band[1]) + 64;
+            if (need > tk.codes_cap) { overflow = true; if (tid == 0) s_need = need; break; }
+          }
+          dp_align<T, kC, kFull>(tk, s, P.tabs, P.ring_rows, smem_raw, band);
+          const int32_t found_row = tk.result[0], found = tk.result[1];
+          if (!have_lb || (found_row > 0 && found >= lb)) break;
+          if (tid == 0) s_retries += 1;
+          have_lb = found_row > 0 && found > kNegBand / 2;
+          lb = found;
+          __syncthreads();
+        }
+        if (overflow) {
+          if (tid == 0) S.err = kWinCodesCap;
+          __syncthreads();
+          break;
+        }
+      } else {
+        dp_align<T, kC, kFull>(tk, s, P.tabs, P.ring_rows, smem_raw, nullptr);
+      }
+      long long t1 = clock64();
+      if (tid < 32) tb_walk_warp(tk, s, band, kC);
+      __syncthreads();
+      long long t2 = clock64();
+      if (tid == 0) {
+        cyc[1] += static_cast<unsigned long long>(t1 - t0);
+        cyc[2] += static_cast<unsigned long long>(t2 - t1);
+        if (m.result[2] < 0 || m.result[0] <= 0) S.err = kWinTraceback;
+        S.last_score = m.result[1];
+        if (m.result[2] > 0) s_steps += static_cast<uint64_t>(m.result[2]);
+        S.last_len = L;
+      }
+      __syncthreads();
+      if (S.err != kWinOk) break;
+      const int32_t np = m.result[2];
+      if (P.pairs_out != nullptr && d.pairs_off >= 0) {   // debug: forward pairs of this sequence
+        int32_t* dst = P.pairs_out + 2 * (d.pairs_off + static_cast<int64_t>(s_pairs));
+        for (int32_t a = tid; a < np; a += T) {
+          dst[2 * a] = m.path[2 * (np - 1 - a)];
+          dst[2 * a + 1] = m.path[2 * (np - 1 - a) + 1];
+        }
+        __syncthreads();
+        if (tid == 0) { P.pair_cnt[d.member_begin + q] = np; s_pairs += static_cast<uint64_t>(np); }
+      }
+      dg_add_alignment(x, m, caps, &S, m.path, np, seq, L);
+      long long t3 = clock64();
+      if (S.err != kWinOk) break;
+      x.one([&]() { dg_toposort_serial(m, caps, &S); });
+      if (tid == 0) {
+        const long long t4 = clock64();
+        cyc[3] += static_cast<unsigned long long>(t3 - t2);
+        cyc[4] += static_cast<unsigned long long>(t4 - t3);
+      }
     }
-    if (threadIdx.x < 32) tb_walk_warp(tk, s, band, kC);
+    // ---- consensus, MSA, result record --------------------------------------------------------
+    __syncthreads();
+    const long long t5 = clock64();
+    __shared__ uint32_t s_cons_len;
+    __shared__ unsigned long long s_out_off;
+    if (tid == 0) { s_cons_len = 0; s_out_off = 0; }
+    __syncthreads();
+    if (S.err == kWinOk && S.nseq > 0) {
+      dg_export(x, m, caps, &S, s, static_cast<uint32_t>(P.ring_rows), true);
+      uint8_t* cons_tmp = reinterpret_cast<uint8_t*>(m.band);
+      const uint64_t V1 = static_cast<uint64_t>(caps.vcap) + 2;
+      x.one([&]() { s_cons_len = dg_consensus_serial(m, &S, m.depth, m.depth + V1, cons_tmp); });
+      uint32_t* head = m.single_before;
+      uint32_t* col_of = reinterpret_cast<uint32_t*>(m.xslot);
+      if (P.want_msa) dg_msa_columns(x, m, &S, head, col_of);
+      x.one([&]() {
+        const uint64_t bytes = (P.want_msa ? static_cast<uint64_t>(S.nseq) * S.msa_cols : 0) + s_cons_len;
+        const unsigned long long need = dg_align(bytes, 16);
+        const unsigned long long at = atomicAdd(P.out_cursor, need);
+        s_out_off = at;
+        if (at + need > P.out_cap) { S.err = kWinOutCap; s_need = need; }
+      });
+      if (S.err == kWinOk) {
+        uint8_t* out = P.out_base + s_out_off;
+        const uint64_t msa_bytes = P.want_msa ? static_cast<uint64_t>(S.nseq) * S.msa_cols : 0;
+        if (P.want_msa) dg_msa_rows(x, m, &S, col_of, m.seq_len, S.nseq, out);
+        for (uint32_t k = tid; k < s_cons_len; k += T) out[msa_bytes + k] = cons_tmp[k];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      WinResult r;
+      r.status = S.err;
+      r.msa_rows = (S.err == kWinOk && P.want_msa) ? S.nseq : 0;
+      r.msa_cols = (S.err == kWinOk && P.want_msa) ? S.msa_cols : 0;
+      r.cons_len = S.err == kWinOk ? s_cons_len : 0;
+      r.out_off = s_out_off;
+      r.n_align = s_nalign; r.retries = s_retries;
+      r.nodes = S.nv; r.edges = S.ne;
+      r.cells = s_cells; r.rows = s_rows; r.exported = s_exported; r.need_bytes = s_need;
+      r.read_bases = s_bases; r.path_steps = s_steps; r.pred_entries = s_preds;
+      cyc[5] += static_cast<unsigned long long>(clock64() - t5);
+      for (int k = 0; k < 8; ++k) r.cyc[k] = cyc[k];
+      P.results[widx] = r;
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0 && slots_per_sm > 1) {
+  if (tid == 0) {
     __threadfence();
-    atomicExch(&slot_flags[my_slot], 0);
+    atomicExch(&P.slot_flags[s_slot], 0);
   }
-}
-
-__global__ void poa_tb_kernel(const PoaTask* __restrict__ tasks, const Scores s, const int n_tasks) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_tasks) return;
-  const PoaTask tk = tasks[idx];
-  const int32_t n = traceback_walk(static_cast<uint32_t>(tk.result[0]), tk.L, tk.codes, tk.w1, tk.w2,
-                                   tk.single_before, tk.col0code, tk.pred_off, tk.preds, tk.node_id, s, tk.path,
-                                   static_cast<int32_t>(tk.path_cap));
-  tk.result[2] = n;
-  tk.result[3] = 0;
 }
 
 }  // namespace
@@ -665,92 +823,50 @@ size_t poa_dp_smem_bytes(int threads, int ring_rows, int cols) {
 
 int poa_dp_cols_per_pass(int threads, int cols) { return threads * poa_cols_per_thread(threads, cols); }
 
-cudaError_t poa_dp_configure(int threads, int ring_rows, int cols) {
-  const int bytes = static_cast<int>(poa_dp_smem_bytes(threads, ring_rows, cols));
-  if (poa_cols_per_thread(threads, cols) == 16)
-    return cudaFuncSetAttribute(poa_dp_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (poa_cols_per_thread(threads, cols) == 4)
-    return cudaFuncSetAttribute(poa_dp_kernel<512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  switch (threads) {
-    case 128: return cudaFuncSetAttribute(poa_dp_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    case 256: return cudaFuncSetAttribute(poa_dp_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    case 512: return cudaFuncSetAttribute(poa_dp_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    default: return cudaErrorInvalidValue;
-  }
-}
+// ---- window kernel launchers ----------------------------------------------------------------
+size_t poa_window_smem_bytes(int threads, int ring_rows, int cols) { return poa_dp_smem_bytes(threads, ring_rows, cols); }
 
-cudaError_t poa_dp_launch(const PoaTask* d_tasks, int n_tasks, const Scores& s, int threads, int ring_rows, int cols,
-                          cudaStream_t stream) {
-  if (n_tasks <= 0) return cudaSuccess;
-  const size_t smem = poa_dp_smem_bytes(threads, ring_rows, cols);
-  const SingleTables tabs = make_single_tables(s);
-  if (poa_cols_per_thread(threads, cols) == 16) {
-    poa_dp_kernel<256, 16><<<n_tasks, 256, smem, stream>>>(d_tasks, s, tabs, ring_rows);
-    return cudaGetLastError();
-  }
-  if (poa_cols_per_thread(threads, cols) == 4) {
-    poa_dp_kernel<512, 4><<<n_tasks, 512, smem, stream>>>(d_tasks, s, tabs, ring_rows);
-    return cudaGetLastError();
-  }
-  switch (threads) {
-    case 128: poa_dp_kernel<128, 8><<<n_tasks, 128, smem, stream>>>(d_tasks, s, tabs, ring_rows); break;
-    case 256: poa_dp_kernel<256, 8><<<n_tasks, 256, smem, stream>>>(d_tasks, s, tabs, ring_rows); break;
-    case 512: poa_dp_kernel<512, 8><<<n_tasks, 512, smem, stream>>>(d_tasks, s, tabs, ring_rows); break;
-    default: return cudaErrorInvalidValue;
-  }
-  return cudaGetLastError();
-}
-
-// Persistent mode needs a fixed number of resident CTAs per SM, enforced by shared memory:
-// one (> 114 KB per CTA) for 512x8, 512x4, 256x16; two (76..113 KB per CTA) for 256x8.
-// Returns that number, 0 if the configuration cannot run persistently.
-int poa_persistent_ctas_per_sm(int threads, int ring_rows, int cols) {
-  const size_t smem = poa_dp_smem_bytes(threads, ring_rows, cols);
+int poa_window_ctas_per_sm(int threads, int ring_rows, int cols) {
+  const size_t smem = poa_window_smem_bytes(threads, ring_rows, cols) + 2048;   // + static shared memory
   const int c = poa_cols_per_thread(threads, cols);
-  if ((threads == 512 || (threads == 256 && c == 16)) && smem > 114 * 1024) return 1;
-  if (threads == 256 && c == 8 && smem > 76 * 1024 && smem <= 113 * 1024) return 2;
-  return 0;
+  if (smem > 227 * 1024) return 0;
+  int by_smem = static_cast<int>((227 * 1024) / (smem + 1024));
+  int cap = 1;
+  if (threads == 128 && c == 8) cap = 4;
+  else if (threads == 256 && c == 8) cap = 2;
+  else if (threads == 256 && c == 16) cap = 1;
+  else if (threads == 512) cap = 1;
+  else return 0;
+  return by_smem < cap ? by_smem : cap;
 }
 
-bool poa_persistent_supported(int threads, int ring_rows, int cols) {
-  return poa_persistent_ctas_per_sm(threads, ring_rows, cols) > 0;
+template <int T, int kC>
+static cudaError_t window_cfg(int bytes) {
+  return cudaFuncSetAttribute(poa_window_kernel<T, kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
-cudaError_t poa_persistent_configure(int threads, int ring_rows, int cols) {
-  if (!poa_persistent_supported(threads, ring_rows, cols)) return cudaErrorInvalidValue;
-  const int bytes = static_cast<int>(poa_dp_smem_bytes(threads, ring_rows, cols));
+cudaError_t poa_window_configure(int threads, int ring_rows, int cols) {
+  if (poa_window_ctas_per_sm(threads, ring_rows, cols) <= 0) return cudaErrorInvalidValue;
+  const int bytes = static_cast<int>(poa_window_smem_bytes(threads, ring_rows, cols));
   const int c = poa_cols_per_thread(threads, cols);
-  if (threads == 512 && c == 4)
-    return cudaFuncSetAttribute(poa_persistent_kernel<512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (threads == 512) return cudaFuncSetAttribute(poa_persistent_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (c == 16) return cudaFuncSetAttribute(poa_persistent_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  return cudaFuncSetAttribute(poa_persistent_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (threads == 128) return window_cfg<128, 8>(bytes);
+  if (threads == 256 && c == 16) return window_cfg<256, 16>(bytes);
+  if (threads == 256) return window_cfg<256, 8>(bytes);
+  if (threads == 512 && c == 4) return window_cfg<512, 4>(bytes);
+  if (threads == 512) return window_cfg<512, 8>(bytes);
+  return cudaErrorInvalidValue;
 }
 
-cudaError_t poa_persistent_launch(const PoaTask* d_tasks, int n_tasks, int* d_counter, uint8_t* slot_base,
-                                  uint64_t slot_bytes, int* slot_flags, int n_sm, const Scores& s, int threads,
-                                  int ring_rows, int cols, cudaStream_t stream) {
-  if (n_tasks <= 0) return cudaSuccess;
-  const size_t smem = poa_dp_smem_bytes(threads, ring_rows, cols);
-  const int spm = poa_persistent_ctas_per_sm(threads, ring_rows, cols);
-  const int grid = n_tasks < n_sm * spm ? n_tasks : n_sm * spm;
-  const SingleTables tabs = make_single_tables(s);
+cudaError_t poa_window_launch(const WinParams& p, int grid, int threads, int cols, cudaStream_t stream) {
+  if (grid <= 0) return cudaSuccess;
+  const size_t smem = poa_window_smem_bytes(threads, p.ring_rows, cols);
   const int c = poa_cols_per_thread(threads, cols);
-  if (threads == 512 && c == 4)
-    poa_persistent_kernel<512, 4><<<grid, 512, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, slot_flags, spm, s, tabs, ring_rows);
-  else if (threads == 512)
-    poa_persistent_kernel<512, 8><<<grid, 512, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, slot_flags, spm, s, tabs, ring_rows);
-  else if (c == 16)
-    poa_persistent_kernel<256, 16><<<grid, 256, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, slot_flags, spm, s, tabs, ring_rows);
-  else
-    poa_persistent_kernel<256, 8><<<grid, 256, smem, stream>>>(d_tasks, n_tasks, d_counter, slot_base, slot_bytes, slot_flags, spm, s, tabs, ring_rows);
-  return cudaGetLastError();
-}
-
-cudaError_t poa_tb_launch(const PoaTask* d_tasks, int n_tasks, const Scores& s, cudaStream_t stream) {
-  if (n_tasks <= 0) return cudaSuccess;
-  const int block = 32;
-  poa_tb_kernel<<<(n_tasks + block - 1) / block, block, 0, stream>>>(d_tasks, s, n_tasks);
+  if (threads == 128) poa_window_kernel<128, 8><<<grid, 128, smem, stream>>>(p);
+  else if (threads == 256 && c == 16) poa_window_kernel<256, 16><<<grid, 256, smem, stream>>>(p);
+  else if (threads == 256) poa_window_kernel<256, 8><<<grid, 256, smem, stream>>>(p);
+  else if (threads == 512 && c == 4) poa_window_kernel<512, 4><<<grid, 512, smem, stream>>>(p);
+  else if (threads == 512) poa_window_kernel<512, 8><<<grid, 512, smem, stream>>>(p);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

@@ -6,37 +6,74 @@ from typing import List, Sequence
 
 import numpy as np
 
-from ._lib import Context, ReadSet, c_vp, load, ptr
+from ._lib import Context, ReadSet, SvsError, c_vp, load, ptr
 
 STAT_NAMES = ["cells", "alignments", "dp_ms", "tb_ms", "wall_ms", "dp_launches", "tb_launches",
-              "h2d_bytes", "d2h_bytes", "algo_bytes", "exported_rows", "rows", "host_wait_ms", "host_merge_ms",
-              "host_plan_ms", "host_pack_ms", "refill_ms", "starved_polls", "launch_ms", "final_ms", "inflight_ms",
-              "h2d_ms", "d2h_ms", "prune_retries"]
+              "h2d_bytes", "d2h_bytes", "algo_bytes", "exported_rows", "rows", "r12", "r13", "r14", "r15", "r16", "r17",
+              "r18", "r19", "r20", "r21", "r22", "prune_retries", "cyc_export", "cyc_dp", "cyc_traceback", "cyc_merge",
+              "cyc_rank", "cyc_finish", "r30", "r31", "failed_groups"]
+N_STATS = len(STAT_NAMES)
+STATUS_TEXT = {1: "graph nodes exceed the largest memory tier", 2: "graph edges exceed the largest memory tier",
+               3: "aligned group of more than 8 distinct letters", 4: "rank-order stack exceeds the memory tier",
+               5: "traceback codes exceed the largest memory tier", 6: "traceback failed",
+               7: "|V| + L beyond the packed score format", 8: "output arena exhausted", 9: "not run",
+               10: "graph node with more than 31 in-edges"}
 DEFAULT_SCORES = dict(m=5, n=-4, g=-8, e=-6, q=-10, c=-4)
 
 
+class PoaJob:
+    """A submitted batch of groups (svs_poa_submit): the window kernel runs on its own stream
+    while the caller issues other work; ``result()`` waits and fetches the outputs."""
+
+    def __init__(self, ctx: Context, reads: ReadSet, groups, algorithm=1, want_msa=True, scores=None):
+        sc = dict(DEFAULT_SCORES)
+        if scores:
+            sc.update(scores)
+        self.ctx, self.reads, self.ng, self.want_msa = ctx, reads, len(groups), want_msa
+        members = np.ascontiguousarray(np.concatenate([np.asarray(g, np.int64) for g in groups])
+                                       if len(groups) else np.zeros(0, np.int64))
+        goff = np.zeros(len(groups) + 1, np.int64)
+        if len(groups):
+            goff[1:] = np.cumsum([len(g) for g in groups])
+        self._res = c_vp()
+        mem = members if members.size else np.zeros(1, np.int64)
+        ctx.check(load().svs_poa_submit(ctx._h, reads._h, ptr(mem), ptr(goff), len(groups), algorithm,
+                                        sc["m"], sc["n"], sc["g"], sc["e"], sc["q"], sc["c"],
+                                        1 if want_msa else 0, ctypes.byref(self._res)))
+
+    def result(self, as_array=False, strict=True):
+        try:
+            self.ctx.check(load().svs_poa_wait(self._res))
+            return _fetch(self._res, self.ng, self.want_msa, as_array, strict)
+        finally:
+            self.close()
+
+    def close(self):
+        if self._res is not None and self._res.value:
+            load().svs_poa_result_free(self._res)
+        self._res = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def poa_groups(ctx: Context, reads: ReadSet, groups: Sequence[Sequence[int]], algorithm: int = 1,
-               want_msa: bool = True, scores=None, as_array: bool = False):
+               want_msa: bool = True, scores=None, as_array: bool = False, strict: bool = True):
     """Align every group (list of read indices, in alignment order) into its own graph.
 
     Returns (consensus list, msa list (list of row strings per group), stats dict).  With
     ``as_array`` every MSA is a (rows, cols) uint8 array of characters instead of strings
-    (views into one buffer: no per-row decoding)."""
-    sc = dict(DEFAULT_SCORES)
-    if scores:
-        sc.update(scores)
-    members = np.ascontiguousarray(np.concatenate([np.asarray(g, np.int64) for g in groups])
-                                   if len(groups) else np.zeros(0, np.int64))
-    goff = np.zeros(len(groups) + 1, np.int64)
-    if len(groups):
-        goff[1:] = np.cumsum([len(g) for g in groups])
-    res = c_vp()
-    mem = members if members.size else np.zeros(1, np.int64)
-    ctx.check(load().svs_poa_batch(ctx._h, reads._h, ptr(mem), ptr(goff), len(groups), algorithm,
-                                   sc["m"], sc["n"], sc["g"], sc["e"], sc["q"], sc["c"],
-                                   1 if want_msa else 0, ctypes.byref(res)))
-    try:
-        ng = len(groups)
+    (views into one buffer: no per-row decoding).  A group the device could not align
+    (``stats["status"][k] != 0``) raises unless ``strict`` is false, in which case its outputs
+    are empty and the other groups are unaffected."""
+    return PoaJob(ctx, reads, groups, algorithm, want_msa, scores).result(as_array=as_array, strict=strict)
+
+
+def _fetch(res, ng, want_msa, as_array, strict):
+    if True:
         clen = np.zeros(max(ng, 1), np.int64)
         rows = np.zeros(max(ng, 1), np.int64)
         cols = np.zeros(max(ng, 1), np.int64)
@@ -44,10 +81,14 @@ def poa_groups(ctx: Context, reads: ReadSet, groups: Sequence[Sequence[int]], al
         cbuf = np.zeros(max(int(clen[:ng].sum()), 1), np.uint8)
         mbuf = np.zeros(max(int((rows[:ng] * cols[:ng]).sum()), 1), np.uint8)
         load().svs_poa_result_copy(res, ptr(cbuf), ptr(mbuf) if want_msa else None)
-        stats = np.zeros(24, np.float64)
-        load().svs_poa_result_stats(res, ptr(stats), 24)
-    finally:
-        load().svs_poa_result_free(res)
+        stats = np.zeros(N_STATS, np.float64)
+        load().svs_poa_result_stats(res, ptr(stats), N_STATS)
+        status = np.zeros(max(ng, 1), np.int32)
+        load().svs_poa_result_status(res, ptr(status))
+        status = status[:ng]
+    if strict and status.any():
+        k = int(np.flatnonzero(status)[0])
+        raise SvsError("svscope_b200: group %d could not be aligned: %s" % (k, STATUS_TEXT.get(int(status[k]), status[k])))
     cons, msas = [], []
     co = mo = 0
     craw, mraw = cbuf.tobytes(), mbuf.tobytes()
@@ -63,7 +104,10 @@ def poa_groups(ctx: Context, reads: ReadSet, groups: Sequence[Sequence[int]], al
             mo += r * c
         else:
             msas.append([])
-    return cons, msas, {k: float(stats[i]) for i, k in enumerate(STAT_NAMES)}
+    out = {k: float(stats[i]) for i, k in enumerate(STAT_NAMES)}
+    out["status"] = status
+    out["copy_bytes"] = float(cbuf.nbytes + (mbuf.nbytes if want_msa else 0))
+    return cons, msas, out
 
 
 def align_pairs(ctx: Context, seqs: Sequence[str]) -> List[np.ndarray]:

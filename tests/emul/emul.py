@@ -13,9 +13,9 @@ _lib = None
 
 def build(force=False):
     srcs = [os.path.join(HERE, "poa_emul.cpp"), os.path.join(HERE, "dgraph_emul.cpp"),
-            os.path.join(ROOT, "svscope_b200", "csrc", "poa_graph.cpp")]
-    deps = srcs + [os.path.join(ROOT, "svscope_b200", "csrc", h)
-                   for h in ("poa_cell.h", "poa_graph.h", "poa_dgraph.h", "poa_task.h")]
+            os.path.join(HERE, "poa_graph.cpp")]
+    deps = srcs + [os.path.join(HERE, "poa_graph.h")] + [os.path.join(ROOT, "svscope_b200", "csrc", h)
+                                                          for h in ("poa_cell.h", "poa_dgraph.h", "poa_task.h")]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w"] + srcs + ["-o", LIB], check=True)

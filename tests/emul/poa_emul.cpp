@@ -10,7 +10,7 @@
 #include <vector>
 
 #include "../../svscope_b200/csrc/poa_cell.h"
-#include "../../svscope_b200/csrc/poa_graph.h"
+#include "poa_graph.h"
 
 using namespace svs;
 

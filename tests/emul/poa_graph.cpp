@@ -4,7 +4,7 @@
 #include <algorithm>
 #include <stdexcept>
 
-#include "poa_cell.h"
+#include "../../svscope_b200/csrc/poa_cell.h"
 
 namespace svs {
 

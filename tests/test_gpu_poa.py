@@ -41,14 +41,13 @@ def _random_group(rng, it, lmax=400):
     return seqs
 
 
-@pytest.mark.parametrize("threads,ring,cols", [(512, 12, 8), (256, 12, 16), (256, 12, 8), (128, 1, 8), (512, 3, 8),
-                                               (128, 24, 8), (256, 2, 16), (512, 24, 4), (512, 5, 4)])
+@pytest.mark.parametrize("threads,ring,cols", [(128, 10, 8), (512, 12, 8), (256, 12, 16), (256, 12, 8), (128, 1, 8),
+                                               (512, 3, 8), (128, 24, 8), (256, 2, 16), (512, 24, 4), (512, 5, 4)])
 def test_alignment_pairs_bit_exact(ctx, oracle, threads, ring, cols):
     """Every alignment (node id, read position) list equals the oracle's, for several CTA
     sizes and ring depths (ring 1 forces almost every non-adjacent predecessor through the
-    exported rows in global memory).  (256, 12, 8) [default: two resident CTAs per SM], (512, 12, 8), (512, 24, 4) and
-    (256, 12, 16) run the persistent kernel (scratch slots, fused traceback); the others take the
-    classic launch path."""
+    exported rows in global memory).  All shapes run the window kernel (graph resident on the
+    device); the default is 128 x 8 with a ring of 10 rows (four resident windows per SM)."""
     from svscope_b200.poa_api import align_pairs
     ctx.set_option("poa_threads", threads)
     ctx.set_option("ring_rows", ring)
@@ -64,8 +63,8 @@ def test_alignment_pairs_bit_exact(ctx, oracle, threads, ring, cols):
                 assert a.shape == b.shape and np.array_equal(a, b)
             o.close()
     finally:
-        ctx.set_option("poa_threads", 256)
-        ctx.set_option("ring_rows", 12)
+        ctx.set_option("poa_threads", 128)
+        ctx.set_option("ring_rows", 10)
         ctx.set_option("poa_cols", 8)
 
 

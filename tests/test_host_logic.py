@@ -422,7 +422,7 @@ def _device_stand_ins(oracle, monkeypatch):
         off[1:] = np.cumsum([len(s) for s in seqs])
         return types.SimpleNamespace(seqs=seqs, off=off, nbytes=int(off[-1]))
 
-    def fake_poa_groups(ctx, reads, groups, algorithm=1, want_msa=True, scores=None, as_array=False):
+    def fake_poa_groups(ctx, reads, groups, algorithm=1, want_msa=True, scores=None, as_array=False, strict=True):
         cons, msas = [], []
         for g in groups:
             c, m = oracle.poa([reads.seqs[i] for i in g], algorithm) if len(g) else ("", [])
@@ -431,7 +431,9 @@ def _device_stand_ins(oracle, monkeypatch):
                 msas.append(np.frombuffer("".join(m).encode(), np.uint8).reshape(len(m), -1) if m else np.zeros((0, 0), np.uint8))
             else:
                 msas.append(m if want_msa else [])
-        return cons, msas, {k: 0.0 for k in poa_api.STAT_NAMES}
+        st = {k: 0.0 for k in poa_api.STAT_NAMES}
+        st["status"] = np.zeros(len(groups), np.int32)
+        return cons, msas, st
 
     def fake_msa_features(ctx, encs, drops, cutoffs):
         out = []
