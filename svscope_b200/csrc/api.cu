@@ -119,6 +119,9 @@ int svs_set_option(svs_ctx* ctx, const char* key, int64_t value) {
   } else if (k == "ring_rows") {
     if (value < 1 || value > 64) return fail(ctx, SVS_ERR_ARG, "ring_rows out of range");
     ctx->ring_rows = static_cast<int>(value);
+  } else if (k == "dp_kernel") {
+    if (value != 1 && value != 2) return fail(ctx, SVS_ERR_ARG, "dp_kernel must be 1 or 2");
+    ctx->dp_kernel = static_cast<int>(value);
   } else if (k == "workers") {
     if (value < 1 || value > 64) return fail(ctx, SVS_ERR_ARG, "workers out of range");
     ctx->workers = static_cast<int>(value);
@@ -153,6 +156,7 @@ int64_t svs_get_option(const svs_ctx* ctx, const char* key) {
   if (k == "ring_rows") return ctx->ring_rows;
   if (k == "poa_cols") return ctx->poa_cols;
   if (k == "prune") return ctx->prune;
+  if (k == "dp_kernel") return ctx->dp_kernel;
   if (k == "workers") return ctx->workers;
   if (k == "lane_jobs") return ctx->lane_jobs;
   if (k == "inflight") return ctx->inflight;

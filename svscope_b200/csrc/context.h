@@ -18,6 +18,7 @@ struct svs_ctx {
   int prune = 1;       // exact score-bound pruning of DP cells (persistent kernel)
   int poa_cols = 8;    // read columns per thread (16 only with 256 threads)
   int ring_rows = 10;
+  int dp_kernel = 2;   // 2: warp-pipelined DP (no CTA barrier per row), 1: barrier-per-row DP
   int workers = 4;
   int64_t arena_mb = 0;
   int lane_jobs = 0;   // alignments per round of a lane (0 = derived)

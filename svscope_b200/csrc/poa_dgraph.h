@@ -81,6 +81,7 @@ struct WinMem {
   uint32_t* single_before;
   int32_t* depth;        // [vcap+1][4]
   int32_t* band;         // [vcap+1][2]
+  uint32_t* coff;        // [vcap+3] code-row offsets of the running alignment
   int32_t* bnd;          // [2][4][vcap+1]
   int32_t* result;       // [4]
   int32_t* path;         // [2 * path_cap]
@@ -129,6 +130,7 @@ SVS_HD uint64_t win_layout(uint8_t* base, uint64_t slot_bytes, const WinCaps& c,
   m->single_before = reinterpret_cast<uint32_t*>(take(4 * (V1 + 1)));
   m->depth = reinterpret_cast<int32_t*>(take(16 * V1));
   m->band = reinterpret_cast<int32_t*>(take(8 * V1));
+  m->coff = reinterpret_cast<uint32_t*>(take(4 * (V1 + 2)));
   m->bnd = reinterpret_cast<int32_t*>(take(32 * V1));
   m->result = reinterpret_cast<int32_t*>(take(64));
   m->path_cap = static_cast<uint32_t>(V + c.lmax + 2);

@@ -1,0 +1,558 @@
+// Warp-pipelined dynamic programme of one sequence-to-graph alignment (included by
+// poa_kernels.cu inside its anonymous namespace).
+//
+// Geometry: a pass covers a strip of T*8 read columns; warp w owns the 256 columns
+// [jb + 256 w, jb + 256 (w + 1)), lane l the 8 columns from jb + 256 w + 8 l on ("chunk").
+// Every warp sweeps the graph rows top to bottom ON ITS OWN: there is no CTA-wide barrier
+// inside a pass.  The only coupling between warps is the horizontal dependency across the
+// 256-column boundary: after the in-warp prefix scans of row i, lane 31 of warp w publishes the
+// state of its last column (A, E, Q, H) in a 64-deep ring in shared memory and then row index i
+// in prog[w]; warp w + 1 starts row i when prog[w] >= i, so the warps run as a skewed
+// pipeline over the rows (anti-diagonal wavefront at warp granularity).  Warp w waits for
+// warp w + 1 only when it is more than 32 rows ahead (ring reuse).  Predecessor rows come
+// from registers (previous row), the warp's private ring of packed rows in shared memory
+// (ring_rows deep, 1 KB per row) or, for rows with a far successor, global memory.
+//
+// Traceback codes: row i stores the chunks [clo_i, chi_i] its band touches, 1 byte per cell
+// (rows with one predecessor) or 2 bytes per cell, at byte offset 8 * coff[i] (exclusive prefix
+// sums, compute_bands2), so the scratch holds exactly the evaluated cells.
+//
+// Cell arithmetic, packed rows and code format: poa_cell.h (unchanged, proven against the
+// five-matrix oracle).
+
+constexpr int kCarryDepth = 64;
+constexpr int kStageCap = 160;   // predecessor entries staged per 32-row batch and warp
+
+struct __align__(16) Carry {
+  int32_t A, E, Q, H;
+};
+
+__host__ __device__ inline size_t dp2_smem_bytes(int threads, int ring_rows) {
+  const int nw = threads / 32;
+  return static_cast<size_t>(threads) * 8 * 4 * ring_rows   // packed-row rings
+         + static_cast<size_t>(nw) * kCarryDepth * sizeof(Carry)
+         + 64                                                   // prog[]
+         + static_cast<size_t>(nw) * kStageCap * 12;            // staged predecessor entries
+}
+
+// Band, chunk range and code offset of every row.  band[2i], band[2i+1] = first / last
+// column (1-based; lo > hi: no cell); coff[i] = offset of the row's codes in units of 8 bytes.
+// Returns (in *need_bytes, written by thread 0 to shared memory by the caller) the total.
+template <int T>
+__device__ void compute_bands2(CtaExec& x, const PoaTask& tk, const Scores& s, int32_t lb, bool have_lb, int32_t* band,
+                               uint32_t* coff, unsigned long long* need_bytes) {
+  const int32_t L = static_cast<int32_t>(tk.L);
+  for (uint32_t i = threadIdx.x; i <= tk.R; i += T) {
+    int32_t lo = 1, hi = L;
+    if (i == 0) { lo = 1; hi = 0; }
+    else if (have_lb) {
+      const int4 d = *(reinterpret_cast<const int4*>(tk.depth) + i);
+      auto ub = [&](int32_t j) { return cell_bound(s, d.x, d.y, d.z, d.w, j, L); };
+      int32_t cand[6] = {1, L, d.x, d.y, L - d.w, L - d.z};
+      int32_t jm = 1, best = INT32_MIN;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int32_t j = min(L, max(1, cand[k]));
+        const int32_t v = ub(j);
+        if (v > best) { best = v; jm = j; }
+      }
+      if (best < lb) {
+        lo = 1; hi = 0;
+      } else {
+        int32_t a = 1, b = jm;
+        while (a < b) { const int32_t mid = (a + b) >> 1; if (ub(mid) >= lb) b = mid; else a = mid + 1; }
+        lo = a;
+        a = jm; b = L;
+        while (a < b) { const int32_t mid = (a + b + 1) >> 1; if (ub(mid) >= lb) a = mid; else b = mid - 1; }
+        hi = a;
+      }
+    }
+    band[2 * i] = lo;
+    band[2 * i + 1] = hi;
+    uint32_t units = 0;   // 8-byte units, rounded to 16 bytes
+    if (lo <= hi) {
+      const uint32_t chunks = static_cast<uint32_t>(((hi - 1) >> 3) - ((lo - 1) >> 3) + 1);
+      const bool single = (tk.pred_off[i + 1] - tk.pred_off[i] == 1);
+      units = single ? ((chunks + 1) & ~1u) : 2 * chunks;
+    }
+    coff[i + 1] = units;
+  }
+  if (threadIdx.x == 0) coff[0] = 0;
+  __syncthreads();
+  x.scan(coff + 1, tk.R + 1);     // coff[i+1] = units of rows 0..i  =>  coff[i] = offset of row i
+  if (threadIdx.x == 0) *need_bytes = 8ull * coff[tk.R + 1] + 64;
+  __syncthreads();
+}
+
+__device__ __forceinline__ int ld_prog(const volatile int* p) { return *p; }
+
+template <int T>
+__device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, const SingleTables& tabs, const int ring_rows,
+                                          unsigned char* smem_raw, const int32_t* __restrict__ band,
+                                          const uint32_t* __restrict__ coff) {
+  constexpr int kC = 8;
+  constexpr int NW = T / 32;
+  const int32_t NEGW = pack_cell(kNegBand, kNeg, kNeg);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int32_t* ring = reinterpret_cast<int32_t*>(smem_raw) + static_cast<size_t>(warp) * ring_rows * 256;
+  Carry* carry_all = reinterpret_cast<Carry*>(smem_raw + static_cast<size_t>(T) * 32 * ring_rows);
+  volatile int* prog = reinterpret_cast<volatile int*>(carry_all + NW * kCarryDepth);
+  int32_t* stage = reinterpret_cast<int32_t*>(const_cast<int*>(prog) + 16) + warp * (kStageCap * 3);
+  int32_t* psrc = stage;                                        // source of the predecessor row
+  uint32_t* pchk = reinterpret_cast<uint32_t*>(stage + kStageCap);   // its chunk range, lo | hi << 16
+  int32_t* pbh = stage + 2 * kStageCap;                         // warp 0: H of the predecessor left of the strip
+  Carry* carry_mine = carry_all + warp * kCarryDepth;
+  const Carry* carry_left = carry_all + (warp > 0 ? warp - 1 : 0) * kCarryDepth;
+
+  const uint32_t R = tk.R, L = tk.L;
+  const uint64_t bstride = static_cast<uint64_t>(R) + 1;
+  int32_t best = INT32_MIN;
+  uint32_t best_row = 0;
+
+  for (uint32_t pass = 0; pass < tk.npass; ++pass) {
+    const uint32_t jb = 1 + pass * tk.strip;
+    const uint32_t je = min(L, jb + tk.strip - 1);
+    const uint32_t j0 = jb + 256u * warp + kC * lane;
+    const bool active = j0 <= je;
+    const int32_t gc = static_cast<int32_t>((j0 - 1) >> 3);                 // my chunk
+    const int32_t wc0 = static_cast<int32_t>((jb - 1) >> 3) + 32 * warp;    // first chunk of my warp
+    const int32_t wc1 = min(wc0 + 31, static_cast<int32_t>((je - 1) >> 3)); // last chunk of my warp inside the strip
+    const int32_t sc0 = static_cast<int32_t>((jb - 1) >> 3);                // first chunk of the strip
+    const bool last_pass = (pass + 1 == tk.npass);
+    const bool owns_end = last_pass && active && (L < j0 + kC);
+    const int c_end = owns_end ? static_cast<int>(L - j0) : -1;
+    const bool writes_bnd = !last_pass && active && (gc == static_cast<int32_t>((je - 1) >> 3));
+    const int32_t* bin = tk.bnd + static_cast<uint64_t>(pass & 1) * 4 * bstride;
+    int32_t* bout = tk.bnd + static_cast<uint64_t>((pass + 1) & 1) * 4 * bstride;
+
+    if (lane == 0) prog[warp] = 0;
+    __syncthreads();
+
+    int32_t rd[kC];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) {
+      const uint32_t j = j0 + c;
+      rd[c] = (active && j <= L) ? static_cast<int32_t>(tk.read[j - 1]) : 0x100;
+    }
+    int32_t wprev[kC];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) wprev[c] = NEGW;
+    int32_t hleft_adj = kNegBand;   // H[i-1][j0-1]
+    uint32_t next_check = 40;
+
+    uint32_t i0 = 1;
+    while (i0 <= R) {
+      // ---- metadata of up to 32 rows, one row per lane ---------------------------------------
+      uint32_t nrows = min(32u, R - i0 + 1);
+      const uint32_t mi = i0 + lane;
+      const bool mvalid = static_cast<uint32_t>(lane) < nrows;
+      int32_t m_lo = 1, m_hi = 0;
+      uint32_t m_poff = 0, m_pend = 0, m_coff = 0, m_info = 0;
+      int32_t m_bA = kNegBand, m_bE = kNeg, m_bQ = kNeg;
+      if (mvalid) {
+        const int2 b = *reinterpret_cast<const int2*>(band + 2 * mi);
+        m_lo = b.x; m_hi = b.y;
+        m_poff = tk.pred_off[mi];
+        m_pend = tk.pred_off[mi + 1];
+        m_coff = coff[mi];
+        m_info = static_cast<uint32_t>(tk.letter[mi]) | (static_cast<uint32_t>(tk.flags[mi]) << 8);
+      }
+      const uint32_t pbase = __shfl_sync(0xffffffffu, m_poff, 0);
+      {   // keep the staged predecessor entries of the batch within kStageCap
+        const unsigned fits = __ballot_sync(0xffffffffu, mvalid && (m_pend - pbase) <= static_cast<uint32_t>(kStageCap));
+        nrows = min(nrows, static_cast<uint32_t>(__popc(fits)));   // m_pend is increasing: a prefix of the lanes
+      }
+      const bool mine = static_cast<uint32_t>(lane) < nrows;
+      const int32_t m_clo = (m_lo - 1) >> 3, m_chi = (m_hi - 1) >> 3;
+      const bool m_inter = mine && m_lo <= m_hi && m_chi >= wc0 && m_clo <= wc1;
+      const unsigned any = __ballot_sync(0xffffffffu, m_inter);
+      if (any == 0) {   // no row of the batch has a cell in my 256 columns
+        if (lane == 31) prog[warp] = static_cast<int>(i0 + nrows - 1);
+        i0 += nrows;
+        continue;
+      }
+      // left boundary of the strip (warp 0): column 0 in the first strip, else the state the
+      // previous strip left behind if the band covered its last chunk
+      if (warp == 0 && mine) {
+        if (pass == 0) {
+          m_bA = tk.h0[mi];
+        } else if (m_lo <= m_hi && m_clo <= sc0 - 1 && m_chi >= sc0 - 1) {
+          m_bA = __ldcg(bin + bstride + mi);
+          m_bE = __ldcg(bin + 2 * bstride + mi);
+          m_bQ = __ldcg(bin + 3 * bstride + mi);
+        }
+      }
+      // ---- stage the predecessor entries of my row --------------------------------------------
+      __syncwarp();
+      bool m_wait = m_inter && warp > 0 && m_clo < wc0;   // does the row read anything the warp on my left produces?
+      if (m_inter) {
+        for (uint32_t e = m_poff; e < m_pend; ++e) {
+          const uint32_t p = tk.preds[e];
+          int32_t src, bh = kNegBand;
+          uint32_t chk;
+          if (p == 0) {
+            src = kSrcRow0;
+            chk = 0xffff0000u;
+          } else {
+            const int2 pb = *reinterpret_cast<const int2*>(band + 2 * p);
+            const int32_t pclo = (pb.x - 1) >> 3, pchi = (pb.y - 1) >> 3;
+            chk = pb.x <= pb.y ? (static_cast<uint32_t>(pclo) | (static_cast<uint32_t>(pchi) << 16)) : 1u;   // 1: lo = 1 > hi = 0
+            if (p + 1 == mi) src = kSrcAdj;
+            else if (mi - p <= static_cast<uint32_t>(ring_rows)) src = static_cast<int32_t>(p % ring_rows);
+            else src = kSrcGlobal | tk.xslot[p];
+            if (warp == 0) {
+              if (pass == 0) bh = tk.h0[p];
+              else if (pb.x <= pb.y && pclo <= sc0 - 1 && pchi >= sc0 - 1) bh = __ldcg(bin + p);
+            } else {
+              bh = static_cast<int32_t>(p);   // warps > 0 look the value up in the left warp's carry ring
+              if (pb.x <= pb.y && pclo <= wc0 - 1 && pchi >= wc0 - 1) m_wait = true;
+            }
+          }
+          psrc[e - pbase] = src;
+          pchk[e - pbase] = chk;
+          pbh[e - pbase] = bh;
+        }
+      }
+      __syncwarp();
+
+      for (uint32_t r = 0; r < nrows; ++r) {
+        if (!((any >> r) & 1u)) continue;
+        const uint32_t i = i0 + r;
+        const int32_t clo = __shfl_sync(0xffffffffu, m_clo, r);
+        const int32_t chi = __shfl_sync(0xffffffffu, m_chi, r);
+        const uint32_t info = __shfl_sync(0xffffffffu, m_info, r);
+        const uint32_t nb = __shfl_sync(0xffffffffu, m_poff, r) - pbase;
+        const uint32_t ne = __shfl_sync(0xffffffffu, m_pend, r) - pbase;
+        const uint32_t row_coff = __shfl_sync(0xffffffffu, m_coff, r);
+        const bool need_left = __shfl_sync(0xffffffffu, static_cast<int>(m_wait), r) != 0;
+        const int32_t letter = static_cast<int32_t>(info & 0xffu);
+        const uint32_t rflags = info >> 8;
+        const bool single = (ne - nb == 1);
+        const bool t_active = active && gc >= clo && gc <= chi;
+
+        // ---- pipeline control -----------------------------------------------------------------
+        Carry cin;
+        cin.A = kNegBand; cin.E = kNeg; cin.Q = kNeg; cin.H = kNegBand;
+        if (warp == 0) {
+          cin.A = __shfl_sync(0xffffffffu, m_bA, r);
+          cin.E = __shfl_sync(0xffffffffu, m_bE, r);
+          cin.Q = __shfl_sync(0xffffffffu, m_bQ, r);
+        } else if (need_left) {
+          if (lane == 0) { while (ld_prog(prog + warp - 1) < static_cast<int>(i)) { } }
+          __syncwarp();
+          __threadfence_block();
+          if (clo < wc0) cin = carry_left[i & (kCarryDepth - 1)];
+        }
+        if (NW > 1 && warp + 1 < NW && i >= next_check) {   // do not lap the consumer of my carry ring
+          if (lane == 0) { while (ld_prog(prog + warp + 1) < static_cast<int>(i) - 32) { } }
+          __syncwarp();
+          next_check = i + 8;
+        }
+
+        // ---- phase 1: fold predecessor rows ---------------------------------------------------
+        CellAcc acc[kC];
+#pragma unroll
+        for (int c = 0; c < kC; ++c) { acc[c].Fm = 0; acc[c].Om = 0; acc[c].D = 0; acc[c].meta = 0; }
+        for (uint32_t e = nb; e < ne; ++e) {
+          const int32_t src = psrc[e];
+          const uint32_t chk = pchk[e];
+          const int32_t pclo = static_cast<int32_t>(chk & 0xffffu), pchi = static_cast<int32_t>(chk >> 16);
+          const bool chunk_ok = gc >= pclo && gc <= pchi;
+          const bool left_ok = gc - 1 >= pclo && gc - 1 <= pchi;
+          int32_t w[kC];
+          int32_t hl;
+          if (src == kSrcRow0) {
+#pragma unroll
+            for (int c = 0; c < kC; ++c) w[c] = pack_cell(row0_h(s, static_cast<int32_t>(j0) + c), kNeg, kNeg);
+            hl = row0_h(s, static_cast<int32_t>(j0) - 1);
+          } else {
+            // H of the predecessor row in the column left of my chunk
+            int32_t hl_warp_edge = kNegBand;   // lane 0: the column belongs to the warp on my left (or the strip boundary)
+            if (warp == 0) hl_warp_edge = pbh[e];
+            if (src == kSrcAdj) {
+#pragma unroll
+              for (int c = 0; c < kC; ++c) w[c] = chunk_ok ? wprev[c] : NEGW;
+              if (warp > 0 && left_ok) hl_warp_edge = carry_left[(i - 1) & (kCarryDepth - 1)].H;
+              hl = (lane == 0) ? hl_warp_edge : (left_ok ? hleft_adj : kNegBand);
+            } else if (src & kSrcGlobal) {
+              const int32_t* row = tk.xrows + static_cast<uint64_t>(src & ~kSrcGlobal) * tk.ldx + 3;
+              if (chunk_ok && active) {
+#pragma unroll
+                for (int q = 0; q < kC / 4; ++q) {
+                  const int4 v = __ldcg(reinterpret_cast<const int4*>(row + j0 + 4 * q));
+                  w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < kC; ++c) w[c] = NEGW;
+              }
+              if (warp > 0 && left_ok) hl_warp_edge = unpack_h(__ldcg(row + j0 - 1));
+              hl = (lane == 0) ? hl_warp_edge : ((left_ok && active) ? unpack_h(__ldcg(row + j0 - 1)) : kNegBand);
+            } else {
+              const int32_t* row = ring + static_cast<size_t>(src) * 256;
+              if (chunk_ok) {
+#pragma unroll
+                for (int q = 0; q < kC / 4; ++q) {
+                  const int4 v = *reinterpret_cast<const int4*>(row + kC * lane + 4 * q);
+                  w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < kC; ++c) w[c] = NEGW;
+              }
+              if (warp > 0 && left_ok) hl_warp_edge = carry_left[static_cast<uint32_t>(pbh[e]) & (kCarryDepth - 1)].H;
+              hl = (lane == 0) ? hl_warp_edge : (left_ok ? unpack_h(row[kC * lane - 1]) : kNegBand);
+            }
+          }
+          if (t_active) {
+            if (single) {
+#pragma unroll
+              for (int c = 0; c < kC; ++c) {
+                cell_pred_single(acc[c], w[c], hl, (letter == rd[c]) ? s.m : s.n, s, tabs);
+                hl = unpack_h(w[c]);
+              }
+            } else {
+              const uint32_t k = e - nb;
+#pragma unroll
+              for (int c = 0; c < kC; ++c) {
+                cell_pred_key(acc[c], k, w[c], hl, (letter == rd[c]) ? s.m : s.n, s, tabs);
+                hl = unpack_h(w[c]);
+              }
+            }
+          }
+        }
+
+        // ---- scan: horizontal gap states across the 256 columns of the warp ---------------------
+        int32_t a7 = kNegBand;
+        int32_t el = kNeg, ql = kNeg, eloc7 = kNeg, qloc7 = kNeg;
+        if (t_active) {
+#pragma unroll
+          for (int c = 0; c < kC; ++c) {
+            const int32_t A = single ? imax(acc[c].D, imax(acc[c].Fm, acc[c].Om))
+                                     : imax(key_value(acc[c].D), key_value(static_cast<int32_t>(acc[c].meta)));
+            if (c == kC - 1) { eloc7 = el; qloc7 = ql; a7 = imax(A, kNegBand); }
+            el = imax(A + s.g, el + s.e);
+            ql = imax(A + s.q, ql + s.c);
+          }
+        }
+        int32_t ein0 = 0, qin0 = 0;
+        if (lane == 0) {   // the state left of the warp enters through lane 0
+          ein0 = imax(cin.A + s.g, cin.E + s.e);
+          qin0 = imax(cin.A + s.q, cin.Q + s.c);
+          el = imax(el, ein0 + kC * s.e);
+          ql = imax(ql, qin0 + kC * s.c);
+        }
+        int32_t ve = el, vq = ql;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int32_t oe = __shfl_up_sync(0xffffffffu, ve, d);
+          const int32_t oq = __shfl_up_sync(0xffffffffu, vq, d);
+          if (lane >= d) {
+            ve = imax(ve, oe + kC * s.e * d);
+            vq = imax(vq, oq + kC * s.c * d);
+          }
+        }
+        int32_t ein = __shfl_up_sync(0xffffffffu, ve, 1);
+        int32_t qin = __shfl_up_sync(0xffffffffu, vq, 1);
+        if (lane == 0) { ein = ein0; qin = qin0; }
+        const int32_t se = imax(ein + (kC - 1) * s.e, eloc7);   // E, Q at my last column
+        const int32_t sq = imax(qin + (kC - 1) * s.c, qloc7);
+        RowCarry cy;
+        cy.A = __shfl_up_sync(0xffffffffu, a7, 1);
+        cy.E = __shfl_up_sync(0xffffffffu, se, 1);
+        cy.Q = __shfl_up_sync(0xffffffffu, sq, 1);
+        if (lane == 0) { cy.A = cin.A; cy.E = cin.E; cy.Q = cin.Q; }
+        cy.H = imax(cy.A, imax(cy.E, cy.Q));
+        hleft_adj = cy.H;
+
+        // ---- publish the state of my warp's last column, then the row index ----------------------
+        if (lane == 31) {
+          if (warp + 1 < NW) {
+            Carry out;
+            out.A = a7; out.E = se; out.Q = sq; out.H = imax(a7, imax(se, sq));
+            carry_mine[i & (kCarryDepth - 1)] = out;
+            __threadfence_block();
+          }
+          prog[warp] = static_cast<int>(i);
+        }
+
+        // ---- phase 2: H, traceback codes, packed row ---------------------------------------------
+        if (t_active) {
+          uint32_t cw[kC / 2];
+          int32_t hsel = INT32_MIN;
+          if (single) {
+#pragma unroll
+            for (int c = 0; c < kC; ++c) {
+              int32_t H;
+              const uint32_t cd = cell_finish_single(acc[c], cy, s, H);
+              H = imax(H, kNegBand); cy.H = H; cy.A = imax(cy.A, kNegBand);   // pruned neighbours must not drift
+              wprev[c] = pack_cell(H, acc[c].Fm, acc[c].Om);
+              if (c & 1) cw[c >> 1] |= cd << 16; else cw[c >> 1] = cd;
+              if (c == c_end) hsel = H;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < kC; ++c) {
+              int32_t H, Fv, Ov;
+              const uint32_t cd = cell_finish_key(acc[c], cy, s, H, Fv, Ov);
+              H = imax(H, kNegBand); cy.H = H; cy.A = imax(cy.A, kNegBand);
+              wprev[c] = pack_cell(H, Fv, Ov);
+              if (c & 1) cw[c >> 1] |= cd << 16; else cw[c >> 1] = cd;
+              if (c == c_end) hsel = H;
+            }
+          }
+          uint8_t* crow = tk.codes + 8ull * row_coff;
+          const uint32_t cidx = static_cast<uint32_t>(gc - clo);
+          if (single) {   // low bytes only
+            const uint32_t b0 = (cw[0] & 0xffu) | ((cw[0] >> 8) & 0xff00u) | ((cw[1] & 0xffu) << 16) | ((cw[1] & 0xff0000u) << 8);
+            const uint32_t b1 = (cw[2] & 0xffu) | ((cw[2] >> 8) & 0xff00u) | ((cw[3] & 0xffu) << 16) | ((cw[3] & 0xff0000u) << 8);
+            *reinterpret_cast<uint2*>(crow + 8ull * cidx) = make_uint2(b0, b1);
+          } else {
+            *reinterpret_cast<uint4*>(crow + 16ull * cidx) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+          }
+          int32_t* rrow = ring + static_cast<size_t>(i % ring_rows) * 256 + kC * lane;
+          *reinterpret_cast<int4*>(rrow) = make_int4(wprev[0], wprev[1], wprev[2], wprev[3]);
+          *reinterpret_cast<int4*>(rrow + 4) = make_int4(wprev[4], wprev[5], wprev[6], wprev[7]);
+          if (rflags & kFlagExport) {
+            int32_t* xrow = tk.xrows + static_cast<uint64_t>(tk.xslot[i]) * tk.ldx + 3;
+            *reinterpret_cast<int4*>(xrow + j0) = make_int4(wprev[0], wprev[1], wprev[2], wprev[3]);
+            *reinterpret_cast<int4*>(xrow + j0 + 4) = make_int4(wprev[4], wprev[5], wprev[6], wprev[7]);
+            if (tid == 0 && pass == 0) xrow[0] = pack_cell(cin.A, kNeg, kNeg);
+          }
+          if (writes_bnd) {
+            bout[i] = cy.H;
+            bout[bstride + i] = cy.A;
+            bout[2 * bstride + i] = cy.E;
+            bout[3 * bstride + i] = cy.Q;
+          }
+          if (owns_end && (rflags & kFlagSink) && hsel > best) {
+            best = hsel;
+            best_row = i;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < kC; ++c) wprev[c] = NEGW;   // this row has no cell in my chunk
+        }
+      }
+      // rows at the end of the batch that were skipped: tell the consumer
+      if (lane == 31) prog[warp] = static_cast<int>(i0 + nrows - 1);
+      i0 += nrows;
+    }
+    if (owns_end) {
+      tk.result[0] = static_cast<int32_t>(best_row);
+      tk.result[1] = best;
+    }
+    __syncthreads();
+  }
+}
+
+// Everything the traceback needs to read (band-limited code rows at 8 * coff[row]).
+struct TbView2 {
+  const uint8_t* codes;
+  const int32_t* band;
+  const uint32_t* coff;
+  const uint16_t* col0code;
+  const uint32_t* pred_off;
+  const uint32_t* preds;
+  const uint32_t* node_id;
+};
+
+__device__ __forceinline__ uint32_t tb2_code_at(const TbView2& v, const Scores& s, uint32_t ii, uint32_t jj) {
+  if (ii == 0) return jj == 0 ? 0u : row0_code(s, static_cast<int32_t>(jj));
+  if (jj == 0) return v.col0code[ii];
+  const uint32_t first = (static_cast<uint32_t>(v.band[2 * ii] - 1) >> 3) << 3;   // first stored column - 1
+  const uint8_t* row = v.codes + 8ull * v.coff[ii];
+  const uint32_t col = jj - 1 - first;
+  if (v.pred_off[ii + 1] - v.pred_off[ii] == 1) return row[col];
+  return reinterpret_cast<const uint16_t*>(row)[col];
+}
+
+// One iteration of the reference's traceback loop at (i, j) != (0, 0) (same decisions as
+// poa_cell.h tb_step, code rows addressed through coff).
+__device__ bool tb2_step(const TbView2& v, const Scores& s, uint32_t& i, uint32_t& j, int32_t& n, int32_t* out_pairs,
+                         int32_t cap) {
+  auto pred_row = [&](uint32_t ii, uint32_t k) -> uint32_t { return k == kNoPred ? 0u : v.preds[v.pred_off[ii] + k]; };
+  const uint32_t cd = tb2_code_at(v, s, i, j);
+  const uint32_t move = cd & 3, ext = (cd >> 2) & 1, km = (cd >> 5) & 31;
+  uint32_t pi, pj;
+  if (move == kMoveDiag) { pi = pred_row(i, km); pj = j - 1; }
+  else if (move == kMoveVert) { pi = pred_row(i, km); pj = j; }
+  else { pi = i; pj = j - 1; }
+  if (n >= cap) return false;
+  out_pairs[2 * n] = (i == pi) ? -1 : static_cast<int32_t>(v.node_id[i]);
+  out_pairs[2 * n + 1] = (j == pj) ? -1 : static_cast<int32_t>(j - 1);
+  ++n;
+  i = pi; j = pj;
+  if (move == kMoveHorz && ext) {
+    while (true) {
+      if (n >= cap) return false;
+      out_pairs[2 * n] = -1;
+      out_pairs[2 * n + 1] = static_cast<int32_t>(j - 1);
+      ++n;
+      --j;
+      if (j == 0 || !((tb2_code_at(v, s, i, j) >> 3) & 1)) break;
+    }
+  } else if (move == kMoveVert && ext) {
+    while (i != 0) {
+      const uint32_t c2 = tb2_code_at(v, s, i, j);
+      const uint32_t stop = (c2 >> 4) & 1, ku = (c2 >> 10) & 31;
+      const uint32_t up = pred_row(i, ku);
+      if (n >= cap) return false;
+      out_pairs[2 * n] = static_cast<int32_t>(v.node_id[i]);
+      out_pairs[2 * n + 1] = -1;
+      ++n;
+      i = up;
+      if (stop || i == 0) break;
+    }
+  }
+  return true;
+}
+
+// Traceback by one warp: the 32 lanes test the cells (i-k, j-k) for "chain row + diagonal move"
+// and the walk advances by the number of leading hits; anything else is one serial step.
+__device__ void tb2_walk_warp(const PoaTask& tk, const Scores& s, const int32_t* band, const uint32_t* coff) {
+  const TbView2 v{tk.codes, band, coff, tk.col0code, tk.pred_off, tk.preds, tk.node_id};
+  const int lane = threadIdx.x & 31;
+  uint32_t i = static_cast<uint32_t>(tk.result[0]), j = tk.L;
+  int32_t n = 0;
+  const int32_t cap = static_cast<int32_t>(tk.path_cap);
+  bool ok = true;
+  while (ok && !(i == 0 && j == 0)) {
+    bool mine = false;
+    int32_t node = 0;
+    if (i > static_cast<uint32_t>(lane) && j > static_cast<uint32_t>(lane)) {
+      const uint32_t r = i - lane, c = j - lane;
+      const int32_t blo = band[2 * r], bhi = band[2 * r + 1];
+      const uint32_t first = blo >= 1 ? ((static_cast<uint32_t>(blo - 1) >> 3) << 3) : 0u;
+      const uint32_t lastc = blo <= bhi ? ((((static_cast<uint32_t>(bhi - 1)) >> 3) << 3) + 8) : 0u;   // one past the last stored column - 1
+      const bool inside = blo <= bhi && c - 1 >= first && c - 1 < lastc;
+      if (inside && (tk.flags[r] & kFlagChain)) {
+        const uint32_t cd = tk.codes[8ull * coff[r] + (c - 1 - first)];
+        if ((cd & 3u) == kMoveDiag) {
+          mine = true;
+          node = static_cast<int32_t>(tk.node_id[r]);
+        }
+      }
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, mine);
+    const int m = __ffs(~hit) - 1;
+    const int run = m < 0 ? 32 : m;
+    if (run > 0) {
+      if (n + run > cap) { ok = false; break; }
+      if (lane < run) {
+        tk.path[2 * (n + lane)] = node;
+        tk.path[2 * (n + lane) + 1] = static_cast<int32_t>(j - lane - 1);
+      }
+      n += run;
+      i -= run;
+      j -= run;
+    } else {
+      if (lane == 0) ok = tb2_step(v, s, i, j, n, tk.path, cap);
+      i = __shfl_sync(0xffffffffu, i, 0);
+      j = __shfl_sync(0xffffffffu, j, 0);
+      n = __shfl_sync(0xffffffffu, n, 0);
+      ok = __shfl_sync(0xffffffffu, static_cast<int>(ok), 0) != 0;
+    }
+  }
+  if (lane == 0) tk.result[2] = ok ? n : -1;
+}

@@ -595,6 +595,8 @@ struct CtaExec {
   }
 };
 
+#include "poa_dp2.cuh"
+
 template <int T, int kC>
 __global__ void __launch_bounds__(T, (T == 128 ? 4 : (T == 256 && kC == 8 ? 2 : 1)))
 poa_window_kernel(const WinParams P) {
@@ -608,6 +610,7 @@ poa_window_kernel(const WinParams P) {
   __shared__ int s_next, s_slot;
   __shared__ uint64_t s_cells, s_rows, s_exported, s_need, s_pairs, s_bases, s_steps, s_preds;
   __shared__ uint32_t s_nalign, s_retries;
+  __shared__ unsigned long long s_need2;
   CtaExec x{warp_tot};
   const int tid = threadIdx.x;
   // scratch slot: any free one (at most n_slots CTAs of this kernel are resident at a time)
@@ -670,6 +673,7 @@ poa_window_kernel(const WinParams P) {
         tk.xrows = reinterpret_cast<int32_t*>(m.dyn);
         tk.codes = m.dyn + xbytes;
         tk.codes_cap = m.dyn_bytes > xbytes ? m.dyn_bytes - xbytes : 0;
+        tk.coff = m.coff;
         tk.bnd = m.bnd; tk.result = m.result; tk.path = m.path; tk.path_cap = m.path_cap;
         const int64_t span = 10ll * (static_cast<int64_t>(R) + L + 2);
         tk.prune = (P.prune && L >= 1024 && R >= 1024 && span < (1 << 21)) ? 1u : 0u;
@@ -679,7 +683,7 @@ poa_window_kernel(const WinParams P) {
         const uint64_t full = n1 * tk.w1 + (static_cast<uint64_t>(R) - n1) * tk.w2 + 64;
         if (S.max_indeg > kMaxIndeg) S.err = kWinIndeg;
         else if (span >= kMaxKeySpan) S.err = kWinScoreSpan;
-        else if (xbytes + 4096 > m.dyn_bytes || (!tk.prune && full > tk.codes_cap)) { S.err = kWinCodesCap; s_need = full + xbytes; }
+        else if (xbytes + 4096 > m.dyn_bytes || (!tk.prune && !(kC == 8 && P.dp_version == 2) && full > tk.codes_cap)) { S.err = kWinCodesCap; s_need = full + xbytes; }
         s_cells += (static_cast<uint64_t>(R) + 1) * (static_cast<uint64_t>(L) + 1);
         s_rows += R;
         s_exported += S.n_export;
@@ -692,6 +696,31 @@ poa_window_kernel(const WinParams P) {
       if (S.err != kWinOk) break;
       t0 = clock64();
       int32_t* band = nullptr;
+      bool v2_overflow = false;
+      if (kC == 8 && P.dp_version == 2) {
+        // warp-pipelined kernel: bands (pruned: from the guessed lower bound; else full rows) and
+        // exact-size code rows; a result below the guess repeats the alignment with the score found
+        int32_t lb = tk.lb_guess;
+        bool have_lb = tk.prune != 0;
+        for (int attempt = 0; attempt < 3; ++attempt) {
+          if (tid == 0) { tk.result[0] = 0; tk.result[1] = INT32_MIN; }
+          compute_bands2<T>(x, tk, s, lb, have_lb, m.band, m.coff, &s_need2);
+          if (s_need2 > tk.codes_cap) { v2_overflow = true; break; }
+          dp2_align<T>(tk, s, P.tabs, P.ring_rows, smem_raw, m.band, m.coff);
+          const int32_t found_row = tk.result[0], found = tk.result[1];
+          if (!have_lb || (found_row > 0 && found >= lb)) break;
+          if (tid == 0) s_retries += 1;
+          have_lb = found_row > 0 && found > kNegBand / 2;
+          lb = found;
+          __syncthreads();
+        }
+        if (v2_overflow) {
+          if (tid == 0) { S.err = kWinCodesCap; s_need = s_need2; }
+          __syncthreads();
+          break;
+        }
+      } else
+      {
       if (tk.prune) {
         // exact pruning with a guessed lower bound (see poa_persistent_kernel)
         band = m.band;
@@ -721,8 +750,12 @@ poa_window_kernel(const WinParams P) {
       } else {
         dp_align<T, kC, kFull>(tk, s, P.tabs, P.ring_rows, smem_raw, nullptr);
       }
+      }
       long long t1 = clock64();
-      if (tid < 32) tb_walk_warp(tk, s, band, kC);
+      if (tid < 32) {
+        if (kC == 8 && P.dp_version == 2) tb2_walk_warp(tk, s, m.band, m.coff);
+        else tb_walk_warp(tk, s, band, kC);
+      }
       __syncthreads();
       long long t2 = clock64();
       if (tid == 0) {
@@ -824,7 +857,11 @@ size_t poa_dp_smem_bytes(int threads, int ring_rows, int cols) {
 int poa_dp_cols_per_pass(int threads, int cols) { return threads * poa_cols_per_thread(threads, cols); }
 
 // ---- window kernel launchers ----------------------------------------------------------------
-size_t poa_window_smem_bytes(int threads, int ring_rows, int cols) { return poa_dp_smem_bytes(threads, ring_rows, cols); }
+size_t poa_window_smem_bytes(int threads, int ring_rows, int cols) {
+  const size_t v1 = poa_dp_smem_bytes(threads, ring_rows, cols);
+  const size_t v2 = poa_cols_per_thread(threads, cols) == 8 ? dp2_smem_bytes(threads, ring_rows) : 0;
+  return v1 > v2 ? v1 : v2;
+}
 
 int poa_window_ctas_per_sm(int threads, int ring_rows, int cols) {
   const size_t smem = poa_window_smem_bytes(threads, ring_rows, cols) + 2048;   // + static shared memory

@@ -41,6 +41,7 @@ struct PoaTask {
   uint32_t prune;             // 1: prune with bands from `lb_guess` (retry inside the kernel if it was too high)
   int32_t lb_guess;           // guessed lower bound of the optimal score
   uint64_t codes_cap;         // bytes available for traceback codes (pruned alignments use band-limited rows)
+  uint32_t* coff;             // [R+2] warp-pipelined kernel: offset of every row's codes, in units of 8 bytes
 };
 
 }  // namespace svs

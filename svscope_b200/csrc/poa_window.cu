@@ -176,6 +176,7 @@ int launch_round(svs_poa_result* r, const std::vector<int>& groups, int tier_idx
   p.prune = ctx->prune;
   p.want_msa = r->want_msa ? 1 : 0;
   p.prune_margin = 0.10f;
+  p.dp_version = ctx->dp_kernel;
   if (const char* pm = getenv("SVS_PRUNE_MARGIN")) p.prune_margin = static_cast<float>(atof(pm));
   const int grid = std::min(n, tier.n_slots);
   SVS_CUDA(ctx, cudaEventRecord(r->ev0, st));

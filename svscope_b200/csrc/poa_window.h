@@ -54,6 +54,7 @@ struct WinParams {
   int prune;
   int want_msa;
   float prune_margin;
+  int dp_version;             // 2: warp-pipelined DP (8 columns per thread), 1: barrier-per-row DP
 };
 
 size_t poa_window_smem_bytes(int threads, int ring_rows, int cols);
