@@ -7,7 +7,7 @@ from svscope_b200.batch import localgraph_batch, upload_windows
 
 nwin = int(os.environ.get("NWIN", 32))
 ctx = _lib.Context(0)
-for k in ("poa_threads", "ring_rows", "workers", "arena_mb", "lane_jobs", "inflight", "streams", "poa_cols"):
+for k in ("poa_threads", "ring_rows", "arena_mb", "poa_cols", "dp_kernel", "prune"):
     if k.upper() in os.environ:
         ctx.set_option(k, int(os.environ[k.upper()]))
 t0 = time.time()
