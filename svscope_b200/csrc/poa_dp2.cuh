@@ -89,7 +89,7 @@ __device__ __forceinline__ int ld_prog(const volatile int* p) { return *p; }
 template <int T>
 __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, const SingleTables& tabs, const int ring_rows,
                                           unsigned char* smem_raw, const int32_t* __restrict__ band,
-                                          const uint32_t* __restrict__ coff) {
+                                          const uint32_t* __restrict__ coff, unsigned long long* eval_chunks) {
   constexpr int kC = 8;
   constexpr int NW = T / 32;
   const int32_t NEGW = pack_cell(kNegBand, kNeg, kNeg);
@@ -108,6 +108,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
   const uint64_t bstride = static_cast<uint64_t>(R) + 1;
   int32_t best = INT32_MIN;
   uint32_t best_row = 0;
+  uint32_t n_chunks = 0;   // evaluated 8-cell chunks of this thread
 
   for (uint32_t pass = 0; pass < tk.npass; ++pass) {
     const uint32_t jb = 1 + pass * tk.strip;
@@ -378,6 +379,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
 
         // ---- phase 2: H, traceback codes, packed row ---------------------------------------------
         if (t_active) {
+          ++n_chunks;
           uint32_t cw[kC / 2];
           int32_t hsel = INT32_MIN;
           if (single) {
@@ -444,6 +446,8 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
     }
     __syncthreads();
   }
+  n_chunks = __reduce_add_sync(0xffffffffu, n_chunks);
+  if (lane == 0 && eval_chunks != nullptr) atomicAdd(eval_chunks, static_cast<unsigned long long>(n_chunks));
 }
 
 // Everything the traceback needs to read (band-limited code rows at 8 * coff[row]).

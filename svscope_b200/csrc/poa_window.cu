@@ -209,7 +209,7 @@ int collect_round(svs_poa_result* r, std::vector<int>* again) {
     r->res[g] = w;
     r->out_buf[g] = buf;
     if (prev.status != kWinPending) {   // a repeated window: keep counting what was spent
-      r->res[g].cells += prev.cells; r->res[g].n_align += prev.n_align; r->res[g].retries += prev.retries;
+      r->res[g].cells += prev.cells; r->res[g].eval_cells += prev.eval_cells; r->res[g].n_align += prev.n_align; r->res[g].retries += prev.retries;
       r->res[g].rows += prev.rows; r->res[g].exported += prev.exported;
       r->res[g].read_bases += prev.read_bases; r->res[g].path_steps += prev.path_steps; r->res[g].pred_entries += prev.pred_entries;
       for (int c = 0; c < 8; ++c) r->res[g].cyc[c] += prev.cyc[c];
@@ -341,6 +341,7 @@ int wait(svs_poa_result* r) {
   std::fill(st, st + 40, 0.0);
   for (const WinResult& w : r->res) {
     st[0] += static_cast<double>(w.cells);
+    st[12] += static_cast<double>(w.eval_cells);
     st[1] += w.n_align;
     st[10] += static_cast<double>(w.exported);
     st[11] += static_cast<double>(w.rows);

@@ -24,6 +24,7 @@ struct WinResult {
   uint32_t n_align, retries;
   uint32_t nodes, edges;
   uint64_t cells;           // nominal DP cells: sum (R + 1)(L + 1)
+  uint64_t eval_cells;      // cells the kernel evaluated (chunks of 8 inside the bands; dp_kernel 2 only)
   uint64_t rows, exported;  // DP rows / rows exported to global memory, summed over the alignments
   uint64_t need_bytes;      // kWinCodesCap: bytes of traceback codes the failing alignment needed
   uint64_t read_bases, path_steps, pred_entries;   // summed over the alignments (algorithmic bytes)

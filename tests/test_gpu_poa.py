@@ -41,7 +41,7 @@ def _random_group(rng, it, lmax=400):
     return seqs
 
 
-@pytest.mark.parametrize("threads,ring,cols,dp", [(128, 10, 8, 2), (512, 12, 8, 2), (256, 12, 16, 1), (256, 12, 8, 2),
+@pytest.mark.parametrize("threads,ring,cols,dp", [(128, 10, 8, 2), (512, 8, 8, 2), (256, 12, 16, 1), (256, 12, 8, 2),
                                                   (128, 1, 8, 2), (512, 3, 8, 2), (128, 24, 8, 2), (256, 2, 16, 1),
                                                   (512, 24, 4, 1), (512, 5, 4, 1), (128, 10, 8, 1), (256, 3, 8, 1),
                                                   (128, 2, 8, 2), (256, 5, 8, 2)])
