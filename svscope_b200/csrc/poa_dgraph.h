@@ -63,7 +63,13 @@ struct WinMem {
   int32_t* e_next;
   int32_t* e_w;
   uint32_t* row_of;      // node -> row (rank + 1)
-  uint32_t* stack;       // toposort stack [vcap]
+  uint32_t* stack;       // toposort stack pool [ecap + 2 vcap]
+  int32_t* f;            // [vcap] smallest node id among the node's descendants-or-self (aligned links included):
+                         //        the node is emitted by the depth-first walk that starts at node f
+  uint32_t* cnt;         // [vcap+2] rank-order scratch: nodes per walk -> first rank of the walk
+  uint32_t* soff;        // [vcap+2] rank-order scratch: stack need per walk -> first stack slot
+  uint32_t* indeg;       // [vcap] number of in-edges
+  uint8_t* stamp;        // [vcap] rank-order scratch: propagation round in which the node is due
   int32_t* at;           // [lmax] merge scratch: node aligned to / chosen for each read position
   int32_t* flag;         // [lmax] merge scratch
   int32_t* path_node;    // [sumlen] node of every base of every merged sequence
@@ -113,7 +119,12 @@ SVS_HD uint64_t win_layout(uint8_t* base, uint64_t slot_bytes, const WinCaps& c,
   m->e_next = reinterpret_cast<int32_t*>(take(4 * E));
   m->e_w = reinterpret_cast<int32_t*>(take(4 * E));
   m->row_of = reinterpret_cast<uint32_t*>(take(4 * V));
-  m->stack = reinterpret_cast<uint32_t*>(take(4 * V));
+  m->stack = reinterpret_cast<uint32_t*>(take(4 * (E + 2 * V)));
+  m->f = reinterpret_cast<int32_t*>(take(4 * V));
+  m->cnt = reinterpret_cast<uint32_t*>(take(4 * (V + 2)));
+  m->soff = reinterpret_cast<uint32_t*>(take(4 * (V + 2)));
+  m->indeg = reinterpret_cast<uint32_t*>(take(4 * V));
+  m->stamp = take(V + 2);
   m->at = reinterpret_cast<int32_t*>(take(4 * L));
   m->flag = reinterpret_cast<int32_t*>(take(4 * L));
   m->path_node = reinterpret_cast<int32_t*>(take(4 * (c.sumlen + 8)));
@@ -149,6 +160,9 @@ struct WinState {
   uint32_t max_indeg, n_export, n_single;
   uint32_t n_new;         // merge: new nodes / edges of the running read
   uint32_t msa_cols;
+  uint32_t chg[2];        // rank order: a propagation round lowered some f (alternating slots)
+  int32_t err_pending;    // error raised inside a parallel phase, filed into err after its barrier
+  uint32_t topo_rounds, topo_serial;   // statistics
   int32_t last_score;
   uint32_t last_len;
 };
@@ -175,6 +189,8 @@ SVS_HD void dg_init_chain(X& x, const WinMem& m, const WinCaps& c, WinState* S, 
       }
       m.node_id[p + 1] = p;
       m.row_of[p] = p + 1;
+      m.f[p] = static_cast<int32_t>(p);   // all descendants have larger ids
+      m.indeg[p] = p > 0 ? 1u : 0u;
       m.path_node[S->path_off + p] = static_cast<int32_t>(p);
     }
   });
@@ -241,12 +257,13 @@ SVS_HD void dg_add_alignment(X& x, const WinMem& m, const WinCaps& c, WinState* 
       const int32_t a = m.at[p];
       m.letter[id] = seq[p];
       m.has_out[id] = 0;
+      m.indeg[id] = 0;
       m.in_head[id] = m.in_tail[id] = -1;
       uint32_t n_mine = 0;
       if (a >= 0) {
         const uint32_t n = m.n_al[a];
         if (n + 1 > static_cast<uint32_t>(kMaxAligned)) {
-          S->err = kWinAlignedCap;
+          S->err_pending = kWinAlignedCap;
         } else {
           for (uint32_t k = 0; k < n; ++k) {
             const int32_t b = m.al[static_cast<uint64_t>(a) * kMaxAligned + k];
@@ -263,6 +280,7 @@ SVS_HD void dg_add_alignment(X& x, const WinMem& m, const WinCaps& c, WinState* 
       m.at[p] = -2 - static_cast<int32_t>(id);   // resolved below (neighbours still read flag[])
     }
   });
+  x.one([&]() { if (S->err_pending) { S->err = S->err_pending; S->err_pending = 0; } });
   if (S->err) return;
   x.run([&](uint32_t tid, uint32_t nt) {
     for (uint32_t p = tid; p < L; p += nt) {
@@ -303,6 +321,7 @@ SVS_HD void dg_add_alignment(X& x, const WinMem& m, const WinCaps& c, WinState* 
       m.e_w[e] = 2;
       if (m.in_tail[head] < 0) m.in_head[head] = e; else m.e_next[m.in_tail[head]] = e;
       m.in_tail[head] = e;
+      m.indeg[head] += 1;
       m.has_out[tail] = 1;
     }
   });
@@ -354,6 +373,7 @@ SVS_HD void dg_toposort_serial(const WinMem& m, const WinCaps& c, WinState* S) {
         }
         if (ready) {
           m.state[cur] = 2;
+          m.f[cur] = static_cast<int32_t>(root);
           if (!m.as_al[cur]) {
             m.node_id[++rank] = cur;
             m.row_of[cur] = rank;
@@ -368,6 +388,189 @@ SVS_HD void dg_toposort_serial(const WinMem& m, const WinCaps& c, WinState* S) {
         }
       }
       if (ready) --top;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same rank order, computed by the whole CTA.
+//
+// The depth-first walk that starts at node u (outer loop over node ids) emits exactly the nodes
+// whose smallest descendant-or-self id (in-edges reversed, aligned links both ways) is u:
+// every ancestor of u that an earlier walk has not emitted.  With f(v) = that id,
+//   * walks are independent: walk u only needs to know which nodes belong to earlier walks
+//     (f < u), so all walks run in parallel, one thread each, with the literal stack
+//     discipline restricted to the nodes with f == u;
+//   * walk u writes ranks [sum of |walk u'| for u' < u, ...): one prefix sum;
+//   * f is maintained incrementally: new descendants only ever lower it.  After a merge the
+//     read's own path gives f(path[p]) <= min over q >= p of f(path[q]) (a suffix minimum over
+//     the read positions), new nodes also take the f of the group they were aligned into, and
+//     the remaining decreases are propagated to in-edge tails and aligned nodes round by
+//     round until nothing changes (they stay local: a lowered f stops at the first ancestor
+//     that already had a smaller one).
+// `path` = node of every position of the read just merged (m.at), n_old = nodes before it.
+// Falls back to the one-thread walk if the propagation does not settle or the stack pool is short.
+template <class X>
+SVS_HD void dg_toposort(X& x, const WinMem& m, const WinCaps& c, WinState* S, uint32_t L, uint32_t n_old) {
+  const uint32_t n = S->nv;
+  const uint32_t pool = c.ecap + 2 * c.vcap;
+  // ---- f of the path nodes ---------------------------------------------------------------------
+  x.run([&](uint32_t tid, uint32_t nt) {
+    for (uint32_t v = tid; v < n; v += nt) m.stamp[v] = 0;
+    for (uint32_t p = tid; p < L; p += nt) {
+      const uint32_t v = static_cast<uint32_t>(m.at[p]);
+      int32_t b;
+      if (v >= n_old) {
+        b = static_cast<int32_t>(v);
+        const uint32_t na = m.n_al[v];
+        for (uint32_t k = 0; k < na; ++k) {
+          const uint32_t a = static_cast<uint32_t>(m.al[static_cast<uint64_t>(v) * kMaxAligned + k]);
+          if (a < n_old && m.f[a] < b) b = m.f[a];   // (aligned nodes created by this read lie elsewhere on the path)
+        }
+      } else {
+        b = m.f[v];
+      }
+      m.flag[p] = b;
+    }
+  });
+  x.suffix_min(m.flag, L);
+  x.run([&](uint32_t tid, uint32_t nt) {
+    for (uint32_t p = tid; p < L; p += nt) {
+      const uint32_t v = static_cast<uint32_t>(m.at[p]);
+      const int32_t g = m.flag[p];
+      if (v >= n_old) { m.f[v] = g; m.stamp[v] = 1; }
+      else if (g < m.f[v]) { m.f[v] = g; m.stamp[v] = 1; }
+    }
+    if (tid == 0) { S->chg[1] = 1; S->chg[0] = 0; S->topo_rounds = 0; }
+  });
+  // ---- propagate the decreases -----------------------------------------------------------------
+  // (round r reads chg[r & 1], which round r - 1 wrote, and writes the other slot)
+  uint32_t round = 1;
+  while (S->chg[round & 1] && round < 250) {
+    x.one([&]() { S->chg[(round + 1) & 1] = 0; });
+    const uint8_t due = static_cast<uint8_t>(round), next = static_cast<uint8_t>(round + 1);
+    x.run([&](uint32_t tid, uint32_t nt) {
+      bool any = false;
+      for (uint32_t v = tid; v < n; v += nt) {
+        if (m.stamp[v] != due) continue;
+        const int32_t fv = m.f[v];
+        for (int32_t e = m.in_head[v]; e >= 0; e = m.e_next[e]) {
+          const uint32_t t = static_cast<uint32_t>(m.e_tail[e]);
+          if (m.f[t] > fv) { x.atomic_min(&m.f[t], fv); m.stamp[t] = next; any = true; }
+        }
+        const uint32_t na = m.n_al[v];
+        for (uint32_t k = 0; k < na; ++k) {
+          const uint32_t a = static_cast<uint32_t>(m.al[static_cast<uint64_t>(v) * kMaxAligned + k]);
+          if (m.f[a] > fv) { x.atomic_min(&m.f[a], fv); m.stamp[a] = next; any = true; }
+        }
+      }
+      if (any) S->chg[(round + 1) & 1] = 1;
+    });
+    ++round;
+  }
+  bool serial = S->chg[round & 1] != 0;
+  // ---- size and stack need of every walk -------------------------------------------------------
+  if (!serial) {
+    x.run([&](uint32_t tid, uint32_t nt) {
+      for (uint32_t v = tid; v <= n; v += nt) { m.cnt[v + 1] = 0; m.soff[v + 1] = 0; }
+      for (uint32_t v = tid; v < n; v += nt) { m.state[v] = 0; m.as_al[v] = 0; }
+      if (tid == 0) { m.cnt[0] = 0; m.soff[0] = 0; }
+    });
+    x.run([&](uint32_t tid, uint32_t nt) {
+      for (uint32_t v = tid; v < n; v += nt) {
+        const uint32_t u = static_cast<uint32_t>(m.f[v]);
+        x.atomic_add(&m.cnt[u + 1], 1u);
+        x.atomic_add(&m.soff[u + 1], m.indeg[v] + m.n_al[v] + (u == v ? 1u : 0u));
+      }
+    });
+    x.scan(m.cnt + 1, n);      // cnt[u]  = nodes of the walks before u  = first rank of walk u
+    x.scan(m.soff + 1, n);     // soff[u] = first stack slot of walk u
+    serial = m.soff[n] > pool;
+  }
+  if (serial) {
+    x.one([&]() { S->topo_serial += 1; dg_toposort_serial(m, c, S); });
+    return;
+  }
+  // ---- the walks ---------------------------------------------------------------------------------
+  x.run([&](uint32_t tid, uint32_t nt) {
+    if (tid == 0) S->topo_rounds = round;
+    for (uint32_t root = tid; root < n; root += nt) {
+      if (static_cast<uint32_t>(m.f[root]) != root) continue;
+      uint32_t rank = m.cnt[root];
+      if (m.cnt[root + 1] - rank == 1) {   // the walk is the node itself
+        m.node_id[rank + 1] = root;
+        continue;
+      }
+      uint32_t* stack = m.stack + m.soff[root];
+      uint32_t top = 0;
+      auto done = [&](uint32_t t) -> bool { return static_cast<uint32_t>(m.f[t]) != root || m.state[t] == 2; };
+      stack[top++] = root;
+      while (top > 0) {
+        const uint32_t cur = stack[top - 1];
+        bool ready = true;
+        if (m.state[cur] != 2) {
+          for (int32_t e = m.in_head[cur]; e >= 0; e = m.e_next[e]) {
+            const uint32_t t = static_cast<uint32_t>(m.e_tail[e]);
+            if (!done(t)) { stack[top++] = t; ready = false; }
+          }
+          const uint32_t na = m.n_al[cur];
+          if (!m.as_al[cur]) {
+            for (uint32_t k = 0; k < na; ++k) {
+              const uint32_t a = static_cast<uint32_t>(m.al[static_cast<uint64_t>(cur) * kMaxAligned + k]);
+              if (!done(a)) { stack[top++] = a; m.as_al[a] = 1; ready = false; }
+            }
+          }
+          if (ready) {
+            m.state[cur] = 2;
+            if (!m.as_al[cur]) {
+              m.node_id[++rank] = cur;
+              for (uint32_t k = 0; k < na; ++k)
+                m.node_id[++rank] = static_cast<uint32_t>(m.al[static_cast<uint64_t>(cur) * kMaxAligned + k]);
+            }
+          } else {
+            m.state[cur] = 1;
+          }
+        }
+        if (ready) --top;
+      }
+    }
+  });
+  x.run([&](uint32_t tid, uint32_t nt) {
+    for (uint32_t r = 1 + tid; r <= n; r += nt) m.row_of[m.node_id[r]] = r;
+  });
+}
+
+// Path-length intervals of every row (nodes on source->row paths, row included: dmin, dmax;
+// nodes on row->sink paths, row excluded: smin, smax), literal one-thread sweeps.
+SVS_HD void dg_depth_forward(const WinMem& m, uint32_t R) {
+  int32_t* dp = m.depth;
+  for (uint32_t i = 1; i <= R; ++i) {
+    int32_t lo = INT32_MAX, hi = 0;
+    for (uint32_t k = m.pred_off[i]; k < m.pred_off[i + 1]; ++k) {
+      const uint32_t p = m.preds[k];
+      const int32_t a = dp[4 * p], b = dp[4 * p + 1];
+      lo = a < lo ? a : lo;
+      hi = b > hi ? b : hi;
+    }
+    dp[4 * i] = lo + 1;
+    dp[4 * i + 1] = hi + 1;
+  }
+}
+
+SVS_HD void dg_depth_backward(const WinMem& m, uint32_t R) {
+  int32_t* dp = m.depth;
+  uint8_t* seen = m.state;   // rank-order scratch is free here
+  for (uint32_t i = 0; i <= R; ++i) { seen[i] = 0; dp[4 * i + 2] = 0; dp[4 * i + 3] = 0; }
+  for (uint32_t i = R; i >= 1; --i) {
+    const int32_t a = dp[4 * i + 2] + 1, b = dp[4 * i + 3] + 1;
+    for (uint32_t k = m.pred_off[i]; k < m.pred_off[i + 1]; ++k) {
+      const uint32_t p = m.preds[k];
+      if (p == 0) continue;
+      if (!seen[p]) { dp[4 * p + 2] = a; dp[4 * p + 3] = b; seen[p] = 1; }
+      else {
+        if (a < dp[4 * p + 2]) dp[4 * p + 2] = a;
+        if (b > dp[4 * p + 3]) dp[4 * p + 3] = b;
+      }
     }
   }
 }
@@ -449,40 +652,11 @@ SVS_HD void dg_export(X& x, const WinMem& m, const WinCaps& c, WinState* S, cons
       m.xslot[i] = (m.r_flags[i] & kFlagExport) ? m.xslot[i] - 1 : -1;
     }
   });
-  // path-length intervals (pruning bounds, poa_cell.h cell_bound) and column-0 scores:
-  // two sequential sweeps over the rank order, run by two threads at the same time
-  x.two(
-      [&]() {
-        int32_t* dp = m.depth;
-        for (uint32_t i = 1; i <= R; ++i) {
-          int32_t lo = INT32_MAX, hi = 0;
-          for (uint32_t k = m.pred_off[i]; k < m.pred_off[i + 1]; ++k) {
-            const uint32_t p = m.preds[k];
-            const int32_t a = dp[4 * p], b = dp[4 * p + 1];
-            lo = a < lo ? a : lo;
-            hi = b > hi ? b : hi;
-          }
-          dp[4 * i] = lo + 1;
-          dp[4 * i + 1] = hi + 1;
-        }
-      },
-      [&]() {
-        int32_t* dp = m.depth;
-        uint8_t* seen = m.state;   // toposort scratch is free here
-        for (uint32_t i = 0; i <= R; ++i) { seen[i] = 0; dp[4 * i + 2] = 0; dp[4 * i + 3] = 0; }
-        for (uint32_t i = R; i >= 1; --i) {
-          const int32_t a = dp[4 * i + 2] + 1, b = dp[4 * i + 3] + 1;
-          for (uint32_t k = m.pred_off[i]; k < m.pred_off[i + 1]; ++k) {
-            const uint32_t p = m.preds[k];
-            if (p == 0) continue;
-            if (!seen[p]) { dp[4 * p + 2] = a; dp[4 * p + 3] = b; seen[p] = 1; }
-            else {
-              if (a < dp[4 * p + 2]) dp[4 * p + 2] = a;
-              if (b > dp[4 * p + 3]) dp[4 * p + 3] = b;
-            }
-          }
-        }
-      });
+  // path-length intervals (pruning bounds, poa_cell.h cell_bound): two sequential sweeps over
+  // the rank order (dg_depth_forward / dg_depth_backward below); the policy decides how to
+  // run them (CPU: one after the other; device: two warps, each with a ring of recent rows in
+  // shared memory)
+  x.depth_sweeps(m, R);
   // column 0: per gap piece the best in-edge tail plus one extension, sources open a fresh
   // gap, i.e. F0 = g + (dmin-1) e, O0 = q + (dmin-1) c with dmin = fewest nodes on a path from
   // a source to the row; the traceback code repeats the engine's equality tests there

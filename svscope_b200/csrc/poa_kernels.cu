@@ -562,6 +562,7 @@ __device__ void tb_walk_warp(const PoaTask& tk, const Scores& s, const int32_t* 
 // device; the host only sees the result record of the window.
 struct CtaExec {
   uint32_t* warp_tot;   // shared memory, 32 words
+  int32_t* sweep_ring;  // shared memory, 2 x 64 x 2 words (depth sweeps)
   template <class F> __device__ __forceinline__ void run(F f) { f(threadIdx.x, blockDim.x); __syncthreads(); }
   template <class F> __device__ __forceinline__ void one(F f) { if (threadIdx.x == 0) f(); __syncthreads(); }
   template <class F, class G> __device__ __forceinline__ void two(F f, G g) {
@@ -569,6 +570,8 @@ struct CtaExec {
     __syncthreads();
   }
   __device__ __forceinline__ void atomic_max(uint32_t* p, uint32_t v) { atomicMax(p, v); }
+  __device__ __forceinline__ void atomic_min(int32_t* p, int32_t v) { atomicMin(p, v); }
+  __device__ __forceinline__ void atomic_add(uint32_t* p, uint32_t v) { atomicAdd(p, v); }
   __device__ void scan(uint32_t* a, uint32_t n) {
     const uint32_t nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     uint32_t carry = 0;
@@ -593,6 +596,112 @@ struct CtaExec {
       __syncthreads();
     }
   }
+  // a[i] = min(a[i..n))
+  __device__ void suffix_min(int32_t* a, uint32_t n) {
+    const uint32_t nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    int32_t* tot = reinterpret_cast<int32_t*>(warp_tot);
+    int32_t carry = INT32_MAX;
+    if (n == 0) return;
+    for (int64_t base = static_cast<int64_t>((n - 1) / nt) * nt; base >= 0; base -= nt) {
+      const uint32_t i = static_cast<uint32_t>(base) + tid;
+      int32_t v = i < n ? a[i] : INT32_MAX;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int32_t o = __shfl_down_sync(0xffffffffu, v, d);
+        if (lane + d < 32) v = min(v, o);
+      }
+      if (lane == 0) tot[warp] = v;
+      __syncthreads();
+      int32_t add = carry, total = INT32_MAX;
+      for (uint32_t w = 0; w < nw; ++w) {
+        const int32_t t = tot[w];
+        if (w > warp) add = min(add, t);
+        total = min(total, t);
+      }
+      if (i < n) a[i] = min(v, add);
+      carry = min(carry, total);
+      __syncthreads();
+    }
+  }
+  // Path-length intervals (dg_depth_forward / dg_depth_backward): warp 0 sweeps forward, warp 1
+  // backward (a CTA of one warp does both in turn).  A row is one step of the warp: the lanes
+  // fetch the row's predecessors in parallel; values of the last 64 rows live in a ring in
+  // shared memory, older ones in global memory.
+  __device__ void depth_sweeps(const WinMem& m, uint32_t R) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    int32_t* dp = m.depth;
+    // partial values of the backward sweep start as "no successor seen"
+    for (uint32_t i = tid; i <= R; i += blockDim.x) { dp[4 * i + 2] = INT32_MAX; dp[4 * i + 3] = -1; }
+    __syncthreads();
+    if (warp == 0) {
+      int32_t* ring = sweep_ring;                       // [64][2]
+      if (lane == 0) { ring[0] = 0; ring[1] = 0; }      // row 0
+      __syncwarp();
+      for (uint32_t i0 = 1; i0 <= R; i0 += 32) {
+        const uint32_t nrows = min(32u, R - i0 + 1);
+        const uint32_t pb = lane < nrows ? m.pred_off[i0 + lane] : 0;
+        const uint32_t pe = lane < nrows ? m.pred_off[i0 + lane + 1] : 0;
+        for (uint32_t r = 0; r < nrows; ++r) {
+          const uint32_t i = i0 + r;
+          const uint32_t b = __shfl_sync(0xffffffffu, pb, r), e = __shfl_sync(0xffffffffu, pe, r);
+          int32_t lo = INT32_MAX, hi = 0;
+          for (uint32_t k = b + lane; k < e; k += 32) {
+            const uint32_t p = m.preds[k];
+            int32_t a, c;
+            if (i - p < 64) { a = ring[2 * (p & 63)]; c = ring[2 * (p & 63) + 1]; }
+            else { a = dp[4 * p]; c = dp[4 * p + 1]; }
+            lo = min(lo, a);
+            hi = max(hi, c);
+          }
+          lo = __reduce_min_sync(0xffffffffu, lo) + 1;
+          hi = __reduce_max_sync(0xffffffffu, hi) + 1;
+          if (lane == 0) {
+            ring[2 * (i & 63)] = lo; ring[2 * (i & 63) + 1] = hi;
+            dp[4 * i] = lo; dp[4 * i + 1] = hi;
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (warp == (nw > 1 ? 1u : 0u)) {
+      int32_t* ring = sweep_ring + 128;                 // [64][2] partial (smin, smax) of rows [i-63, i]
+      for (uint32_t k = lane; k < 64; k += 32) { ring[2 * k] = INT32_MAX; ring[2 * k + 1] = -1; }
+      __syncwarp();
+      for (uint32_t i1 = R; i1 >= 1; i1 -= min(i1, 32u)) {
+        // rows i1, i1-1, ... (up to 32), lane l holds the predecessor range of row i1 - l
+        const uint32_t nrows = min(32u, i1);
+        const uint32_t pb = lane < nrows ? m.pred_off[i1 - lane] : 0;
+        const uint32_t pe = lane < nrows ? m.pred_off[i1 - lane + 1] : 0;
+        for (uint32_t r = 0; r < nrows; ++r) {
+          const uint32_t i = i1 - r;
+          const uint32_t b = __shfl_sync(0xffffffffu, pb, r), e = __shfl_sync(0xffffffffu, pe, r);
+          int32_t lo = ring[2 * (i & 63)], hi = ring[2 * (i & 63) + 1];
+          if (lo == INT32_MAX) { lo = 0; hi = 0; }   // no successor
+          const int32_t a = lo + 1, c = hi + 1;
+          __syncwarp();
+          if (lane == 0) { dp[4 * i + 2] = lo; dp[4 * i + 3] = hi; }
+          for (uint32_t k = b + lane; k < e; k += 32) {   // the predecessors of a row are distinct rows
+            const uint32_t p = m.preds[k];
+            if (p == 0) continue;
+            if (i - p < 64) {
+              ring[2 * (p & 63)] = min(ring[2 * (p & 63)], a);
+              ring[2 * (p & 63) + 1] = max(ring[2 * (p & 63) + 1], c);
+            } else {
+              dp[4 * p + 2] = min(dp[4 * p + 2], a);
+              dp[4 * p + 3] = max(dp[4 * p + 3], c);
+            }
+          }
+          __syncwarp();
+          // the slot now belongs to row i - 64: start from what successors 64 or more rows away left for it
+          if (lane == 0 && i > 64) { ring[2 * (i & 63)] = dp[4 * (i - 64) + 2]; ring[2 * (i & 63) + 1] = dp[4 * (i - 64) + 3]; }
+          __syncwarp();
+        }
+        if (i1 <= 32) break;
+      }
+      if (lane == 0) { dp[2] = 0; dp[3] = 0; }
+    }
+    __syncthreads();
+  }
 };
 
 #include "poa_dp2.cuh"
@@ -611,7 +720,8 @@ poa_window_kernel(const WinParams P) {
   __shared__ uint64_t s_cells, s_rows, s_exported, s_need, s_pairs, s_bases, s_steps, s_preds;
   __shared__ uint32_t s_nalign, s_retries;
   __shared__ unsigned long long s_need2, s_eval;
-  CtaExec x{warp_tot};
+  __shared__ int32_t sweep_ring[256];
+  CtaExec x{warp_tot, sweep_ring};
   const int tid = threadIdx.x;
   // scratch slot: any free one (at most n_slots CTAs of this kernel are resident at a time)
   if (tid == 0) {
@@ -637,6 +747,7 @@ poa_window_kernel(const WinParams P) {
       S.err = fixed + 4096 > P.slot_bytes ? kWinNodeCap : kWinOk;
       S.max_indeg = 1; S.n_export = S.n_single = S.n_new = S.msa_cols = 0;
       S.last_score = 0; S.last_len = 0;
+      S.err_pending = 0; S.topo_serial = 0; S.topo_rounds = 0; S.chg[0] = S.chg[1] = 0;
       for (int k = 0; k < 8; ++k) cyc[k] = 0;
       s_cells = s_rows = s_exported = s_need = s_pairs = s_bases = s_steps = s_preds = 0;
       s_nalign = s_retries = 0;
@@ -779,10 +890,11 @@ poa_window_kernel(const WinParams P) {
         __syncthreads();
         if (tid == 0) { P.pair_cnt[d.member_begin + q] = np; s_pairs += static_cast<uint64_t>(np); }
       }
+      const uint32_t n_old = S.nv;
       dg_add_alignment(x, m, caps, &S, m.path, np, seq, L);
       long long t3 = clock64();
       if (S.err != kWinOk) break;
-      x.one([&]() { dg_toposort_serial(m, caps, &S); });
+      dg_toposort(x, m, caps, &S, L, n_old);
       if (tid == 0) {
         const long long t4 = clock64();
         cyc[3] += static_cast<unsigned long long>(t3 - t2);

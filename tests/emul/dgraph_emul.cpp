@@ -5,6 +5,7 @@
 // CPU emulation of the kernel arithmetic (poa_emul.cpp).  Not shipped.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -29,7 +30,11 @@ struct SeqExec {
   template <class F> void one(F f) { f(); }
   template <class F, class G> void two(F f, G g) { g(); f(); }
   void scan(uint32_t* a, uint32_t n) { for (uint32_t i = 1; i < n; ++i) a[i] += a[i - 1]; }
+  void depth_sweeps(const WinMem& m, uint32_t R) { dg_depth_backward(m, R); dg_depth_forward(m, R); }
   void atomic_max(uint32_t* p, uint32_t v) { if (v > *p) *p = v; }
+  void atomic_min(int32_t* p, int32_t v) { if (v < *p) *p = v; }
+  void atomic_add(uint32_t* p, uint32_t v) { *p += v; }
+  void suffix_min(int32_t* a, uint32_t n) { for (uint32_t i = n; i-- > 1;) if (a[i] < a[i - 1]) a[i - 1] = a[i]; }
 };
 
 template <class T>
@@ -74,6 +79,7 @@ extern "C" int dgraph_emul_check(const uint8_t* seqs, const int64_t* off, int n_
   void* emu = emu_new(ring_rows);
   std::vector<uint32_t> merged_len;
   bool ok = true;
+  const bool serial_rank = tight_caps != 0;   // flag reused: 1 = literal one-thread rank order
   for (int k = 0; k < n_seqs && ok; ++k) {
     const uint8_t* seq = seqs + off[k];
     const uint32_t L = static_cast<uint32_t>(off[k + 1] - off[k]);
@@ -90,8 +96,12 @@ extern "C" int dgraph_emul_check(const uint8_t* seqs, const int64_t* off, int n_
         rev[2 * a] = nodes[np - 1 - a];
         rev[2 * a + 1] = pos[np - 1 - a];
       }
+      const uint32_t n_old = S.nv;
       dg_add_alignment(x, m, caps, &S, rev.data(), static_cast<int32_t>(np), seq, L);
-      if (!S.err) dg_toposort_serial(m, caps, &S);
+      if (!S.err) {
+        if (serial_rank) dg_toposort_serial(m, caps, &S);
+        else dg_toposort(x, m, caps, &S, L, n_old);
+      }
     }
     merged_len.push_back(L);
     if (S.err) { msg = "device graph error " + std::to_string(S.err); ok = false; break; }
@@ -151,7 +161,7 @@ extern "C" int dgraph_emul_check(const uint8_t* seqs, const int64_t* off, int n_
       }
     }
   }
-  (void)tight_caps;
+  if (getenv("DGRAPH_DEBUG")) std::fprintf(stderr, "nodes %u serial fallbacks %u last rounds %u\n", S.nv, S.topo_serial, S.topo_rounds);
   emu_free(emu);
   if (msg_out && msg_cap > 0) {
     std::snprintf(msg_out, static_cast<size_t>(msg_cap), "%s", msg.c_str());

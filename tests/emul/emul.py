@@ -58,14 +58,15 @@ def lib():
     return _lib
 
 
-def dgraph_check(seqs, ring_rows=4, n_threads=128):
+def dgraph_check(seqs, ring_rows=4, n_threads=128, serial_rank=False):
     """Runs the device-resident graph code (poa_dgraph.h) on the CPU over the sequence group and
     compares every array with the host graph after every read.  Returns '' or the first difference."""
     enc = [s.encode() for s in seqs]
     off = np.zeros(len(enc) + 1, np.int64)
     off[1:] = np.cumsum([len(b) for b in enc])
     msg = ctypes.create_string_buffer(512)
-    rc = lib().dgraph_emul_check(b"".join(enc), off.ctypes.data, len(enc), ring_rows, n_threads, 0, msg, 512)
+    rc = lib().dgraph_emul_check(b"".join(enc), off.ctypes.data, len(enc), ring_rows, n_threads,
+                                 1 if serial_rank else 0, msg, 512)
     return "" if rc == 0 else (msg.value.decode() or "mismatch")
 
 
