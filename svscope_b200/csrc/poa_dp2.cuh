@@ -110,7 +110,17 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
   uint32_t best_row = 0;
   uint32_t n_chunks = 0;   // evaluated 8-cell chunks of this thread
 
+  // progress of a warp = pass * (R + 1) + last row done: the passes of different warps overlap
+  // (warp 0 starts strip p + 1 while the other warps are still in strip p); the strip boundary
+  // travels through global memory (bnd), guarded by the progress of the warp that owns the last
+  // chunk of the strip
+  if (lane == 0) prog[warp] = 0;
+  __syncthreads();
+  const int wlast = static_cast<int>(((tk.strip >> 3) - 1) >> 5);   // warp that owns the last chunk of a full strip
+  int next_check = 40;   // (absolute progress) next row at which I make sure not to lap the consumer of my carry ring
+
   for (uint32_t pass = 0; pass < tk.npass; ++pass) {
+    const int pbase_prog = static_cast<int>(pass * (R + 1));
     const uint32_t jb = 1 + pass * tk.strip;
     const uint32_t je = min(L, jb + tk.strip - 1);
     const uint32_t j0 = jb + 256u * warp + kC * lane;
@@ -126,9 +136,6 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
     const int32_t* bin = tk.bnd + static_cast<uint64_t>(pass & 1) * 4 * bstride;
     int32_t* bout = tk.bnd + static_cast<uint64_t>((pass + 1) & 1) * 4 * bstride;
 
-    if (lane == 0) prog[warp] = 0;
-    __syncthreads();
-
     int32_t rd[kC];
 #pragma unroll
     for (int c = 0; c < kC; ++c) {
@@ -139,7 +146,6 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
 #pragma unroll
     for (int c = 0; c < kC; ++c) wprev[c] = NEGW;
     int32_t hleft_adj = kNegBand;   // H[i-1][j0-1]
-    uint32_t next_check = 40;
 
     uint32_t i0 = 1;
     while (i0 <= R) {
@@ -168,12 +174,18 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
       const bool m_inter = mine && m_lo <= m_hi && m_chi >= wc0 && m_clo <= wc1;
       const unsigned any = __ballot_sync(0xffffffffu, m_inter);
       if (any == 0) {   // no row of the batch has a cell in my 256 columns
-        if (lane == 31) prog[warp] = static_cast<int>(i0 + nrows - 1);
+        if (lane == 31) prog[warp] = pbase_prog + static_cast<int>(i0 + nrows - 1);
         i0 += nrows;
         continue;
       }
       // left boundary of the strip (warp 0): column 0 in the first strip, else the state the
       // previous strip left behind if the band covered its last chunk
+      if (warp == 0 && pass > 0) {   // the previous strip must have passed the rows of this batch
+        const int need = static_cast<int>((pass - 1) * (R + 1) + i0 + nrows - 1);
+        if (lane == 0) { while (ld_prog(prog + wlast) < need) { } }
+        __syncwarp();
+        __threadfence_block();
+      }
       if (warp == 0 && mine) {
         if (pass == 0) {
           m_bA = tk.h0[mi];
@@ -238,16 +250,16 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
           cin.A = __shfl_sync(0xffffffffu, m_bA, r);
           cin.E = __shfl_sync(0xffffffffu, m_bE, r);
           cin.Q = __shfl_sync(0xffffffffu, m_bQ, r);
-        } else if (need_left) {
-          if (lane == 0) { while (ld_prog(prog + warp - 1) < static_cast<int>(i)) { } }
+        } else if (need_left) {   // predecessor rows left of my span: the left warp must have done row i - 1
+          if (lane == 0) { while (ld_prog(prog + warp - 1) < pbase_prog + static_cast<int>(i) - 1) { } }
           __syncwarp();
           __threadfence_block();
-          if (clo < wc0) cin = carry_left[i & (kCarryDepth - 1)];
         }
-        if (NW > 1 && warp + 1 < NW && i >= next_check) {   // do not lap the consumer of my carry ring
-          if (lane == 0) { while (ld_prog(prog + warp + 1) < static_cast<int>(i) - 32) { } }
+        const int abs_i = pbase_prog + static_cast<int>(i);   // carry-ring slots are indexed by absolute progress
+        if (NW > 1 && warp + 1 < NW && abs_i >= next_check) {
+          if (lane == 0) { while (ld_prog(prog + warp + 1) < abs_i - 32) { } }
           __syncwarp();
-          next_check = i + 8;
+          next_check = abs_i + 8;
         }
 
         // ---- phase 1: fold predecessor rows ---------------------------------------------------
@@ -273,7 +285,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
             if (src == kSrcAdj) {
 #pragma unroll
               for (int c = 0; c < kC; ++c) w[c] = chunk_ok ? wprev[c] : NEGW;
-              if (warp > 0 && left_ok) hl_warp_edge = carry_left[(i - 1) & (kCarryDepth - 1)].H;
+              if (warp > 0 && left_ok) hl_warp_edge = carry_left[(abs_i - 1) & (kCarryDepth - 1)].H;
               hl = (lane == 0) ? hl_warp_edge : (left_ok ? hleft_adj : kNegBand);
             } else if (src & kSrcGlobal) {
               const int32_t* row = tk.xrows + static_cast<uint64_t>(src & ~kSrcGlobal) * tk.ldx + 3;
@@ -301,7 +313,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
 #pragma unroll
                 for (int c = 0; c < kC; ++c) w[c] = NEGW;
               }
-              if (warp > 0 && left_ok) hl_warp_edge = carry_left[static_cast<uint32_t>(pbh[e]) & (kCarryDepth - 1)].H;
+              if (warp > 0 && left_ok) hl_warp_edge = carry_left[static_cast<uint32_t>(pbase_prog + pbh[e]) & (kCarryDepth - 1)].H;
               hl = (lane == 0) ? hl_warp_edge : (left_ok ? unpack_h(row[kC * lane - 1]) : kNegBand);
             }
           }
@@ -336,6 +348,12 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
             ql = imax(A + s.q, ql + s.c);
           }
         }
+        if (warp > 0 && need_left) {   // the scan needs the left warp's state of THIS row
+          if (lane == 0) { while (ld_prog(prog + warp - 1) < pbase_prog + static_cast<int>(i)) { } }
+          __syncwarp();
+          __threadfence_block();
+          if (clo < wc0) cin = carry_left[abs_i & (kCarryDepth - 1)];
+        }
         int32_t ein0 = 0, qin0 = 0;
         if (lane == 0) {   // the state left of the warp enters through lane 0
           ein0 = imax(cin.A + s.g, cin.E + s.e);
@@ -366,15 +384,23 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
         cy.H = imax(cy.A, imax(cy.E, cy.Q));
         hleft_adj = cy.H;
 
-        // ---- publish the state of my warp's last column, then the row index ----------------------
+        // ---- publish the state of my warp's last column (or of the strip's last column, through
+        //      global memory, for the next strip), then the row index ---------------------------------
+        if (writes_bnd && t_active) {
+          bout[i] = imax(a7, imax(se, sq));
+          bout[bstride + i] = a7;
+          bout[2 * bstride + i] = se;
+          bout[3 * bstride + i] = sq;
+        }
+        if (warp == wlast) __syncwarp();
         if (lane == 31) {
           if (warp + 1 < NW) {
             Carry out;
             out.A = a7; out.E = se; out.Q = sq; out.H = imax(a7, imax(se, sq));
-            carry_mine[i & (kCarryDepth - 1)] = out;
-            __threadfence_block();
+            carry_mine[abs_i & (kCarryDepth - 1)] = out;
           }
-          prog[warp] = static_cast<int>(i);
+          __threadfence_block();
+          prog[warp] = abs_i;
         }
 
         // ---- phase 2: H, traceback codes, packed row ---------------------------------------------
@@ -421,12 +447,6 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
             *reinterpret_cast<int4*>(xrow + j0 + 4) = make_int4(wprev[4], wprev[5], wprev[6], wprev[7]);
             if (tid == 0 && pass == 0) xrow[0] = pack_cell(cin.A, kNeg, kNeg);
           }
-          if (writes_bnd) {
-            bout[i] = cy.H;
-            bout[bstride + i] = cy.A;
-            bout[2 * bstride + i] = cy.E;
-            bout[3 * bstride + i] = cy.Q;
-          }
           if (owns_end && (rflags & kFlagSink) && hsel > best) {
             best = hsel;
             best_row = i;
@@ -437,15 +457,15 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
         }
       }
       // rows at the end of the batch that were skipped: tell the consumer
-      if (lane == 31) prog[warp] = static_cast<int>(i0 + nrows - 1);
+      if (lane == 31) prog[warp] = pbase_prog + static_cast<int>(i0 + nrows - 1);
       i0 += nrows;
     }
     if (owns_end) {
       tk.result[0] = static_cast<int32_t>(best_row);
       tk.result[1] = best;
     }
-    __syncthreads();
   }
+  __syncthreads();
   n_chunks = __reduce_add_sync(0xffffffffu, n_chunks);
   if (lane == 0 && eval_chunks != nullptr) atomicAdd(eval_chunks, static_cast<unsigned long long>(n_chunks));
 }
