@@ -25,7 +25,7 @@ def _newer(src, dst):
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
-    headers = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".h")]
+    headers = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(PKG), "include", "svscope_b200.h"))
     hdr_time = max(os.path.getmtime(h) for h in headers)
     objs = []
