@@ -33,6 +33,10 @@ for cfg in os.environ.get("CFGS", "128,10,2;256,10,2;128,10,1").split(";"):
         print("cfg T=%d ring=%d dp=%d: %.2fs wall, kernel %.0f ms, %d launches, %.1f nominal GCUPS, evaluated %.1f%%, failed %d, retries %d | ms/alignment (thread 0): %s"
               % (t, ring, dp, dt, st["dp_ms"], st["dp_launches"], st["cells"] / dt / 1e9, 100 * st["eval_cells"] / max(1.0, st["cells"]), st["failed_groups"], st["prune_retries"],
                  " ".join("%s %.2f" % kv for kv in ph.items())), flush=True)
+        wl = max(1.0, st["wcyc_loop"] + st["wcyc_wait_end"])
+        print("    warps in the DP: polling left %.1f%%, polling right/boundary %.1f%%, waiting at the end %.1f%%, working %.1f%%"
+              % (100 * st["wcyc_wait_left"] / wl, 100 * st["wcyc_wait_right"] / wl, 100 * st["wcyc_wait_end"] / wl,
+                 100 * (st["wcyc_loop"] - st["wcyc_wait_left"] - st["wcyc_wait_right"]) / wl), flush=True)
         if ref is None:
             ref = (cons, [m.tobytes() for m in msas])
         else:

@@ -117,6 +117,8 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
   if (lane == 0) prog[warp] = 0;
   __syncthreads();
   const int wlast = static_cast<int>(((tk.strip >> 3) - 1) >> 5);   // warp that owns the last chunk of a full strip
+  long long t_wait_left = 0, t_wait_flow = 0, t_wait_bnd = 0;   // cycles lane 0 spent polling (per warp)
+  const long long t_begin = clock64();
   int next_check = 40;   // (absolute progress) next row at which I make sure not to lap the consumer of my carry ring
 
   for (uint32_t pass = 0; pass < tk.npass; ++pass) {
@@ -182,7 +184,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
       // previous strip left behind if the band covered its last chunk
       if (warp == 0 && pass > 0) {   // the previous strip must have passed the rows of this batch
         const int need = static_cast<int>((pass - 1) * (R + 1) + i0 + nrows - 1);
-        if (lane == 0) { while (ld_prog(prog + wlast) < need) { } }
+        if (lane == 0) { const long long t0 = clock64(); while (ld_prog(prog + wlast) < need) { } t_wait_bnd += clock64() - t0; }
         __syncwarp();
         __threadfence_block();
       }
@@ -251,13 +253,13 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
           cin.E = __shfl_sync(0xffffffffu, m_bE, r);
           cin.Q = __shfl_sync(0xffffffffu, m_bQ, r);
         } else if (need_left) {   // predecessor rows left of my span: the left warp must have done row i - 1
-          if (lane == 0) { while (ld_prog(prog + warp - 1) < pbase_prog + static_cast<int>(i) - 1) { } }
+          if (lane == 0) { const long long t0 = clock64(); while (ld_prog(prog + warp - 1) < pbase_prog + static_cast<int>(i) - 1) { } t_wait_left += clock64() - t0; }
           __syncwarp();
           __threadfence_block();
         }
         const int abs_i = pbase_prog + static_cast<int>(i);   // carry-ring slots are indexed by absolute progress
         if (NW > 1 && warp + 1 < NW && abs_i >= next_check) {
-          if (lane == 0) { while (ld_prog(prog + warp + 1) < abs_i - 32) { } }
+          if (lane == 0) { const long long t0 = clock64(); while (ld_prog(prog + warp + 1) < abs_i - 32) { } t_wait_flow += clock64() - t0; }
           __syncwarp();
           next_check = abs_i + 8;
         }
@@ -349,7 +351,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
           }
         }
         if (warp > 0 && need_left) {   // the scan needs the left warp's state of THIS row
-          if (lane == 0) { while (ld_prog(prog + warp - 1) < pbase_prog + static_cast<int>(i)) { } }
+          if (lane == 0) { const long long t0 = clock64(); while (ld_prog(prog + warp - 1) < pbase_prog + static_cast<int>(i)) { } t_wait_left += clock64() - t0; }
           __syncwarp();
           __threadfence_block();
           if (clo < wc0) cin = carry_left[abs_i & (kCarryDepth - 1)];
@@ -465,9 +467,16 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
       tk.result[1] = best;
     }
   }
+  const long long t_done = clock64();
   __syncthreads();
   n_chunks = __reduce_add_sync(0xffffffffu, n_chunks);
-  if (lane == 0 && eval_chunks != nullptr) atomicAdd(eval_chunks, static_cast<unsigned long long>(n_chunks));
+  if (lane == 0 && eval_chunks != nullptr) {
+    atomicAdd(eval_chunks, static_cast<unsigned long long>(n_chunks));
+    atomicAdd(eval_chunks + 1, static_cast<unsigned long long>(t_done - t_begin));        // busy + polling, per warp
+    atomicAdd(eval_chunks + 2, static_cast<unsigned long long>(t_wait_left));
+    atomicAdd(eval_chunks + 3, static_cast<unsigned long long>(t_wait_flow + t_wait_bnd));
+    atomicAdd(eval_chunks + 4, static_cast<unsigned long long>(clock64() - t_done));        // waiting for the slowest warp at the end
+  }
 }
 
 // Everything the traceback needs to read (band-limited code rows at 8 * coff[row]).

@@ -719,7 +719,7 @@ poa_window_kernel(const WinParams P) {
   __shared__ int s_next, s_slot;
   __shared__ uint64_t s_cells, s_rows, s_exported, s_need, s_pairs, s_bases, s_steps, s_preds;
   __shared__ uint32_t s_nalign, s_retries;
-  __shared__ unsigned long long s_need2, s_eval;
+  __shared__ unsigned long long s_need2, s_eval[5];
   __shared__ int32_t sweep_ring[256];
   CtaExec x{warp_tot, sweep_ring};
   const int tid = threadIdx.x;
@@ -751,7 +751,7 @@ poa_window_kernel(const WinParams P) {
       for (int k = 0; k < 8; ++k) cyc[k] = 0;
       s_cells = s_rows = s_exported = s_need = s_pairs = s_bases = s_steps = s_preds = 0;
       s_nalign = s_retries = 0;
-      s_eval = 0;
+      for (int k = 0; k < 5; ++k) s_eval[k] = 0;
     }
     __syncthreads();
     for (uint32_t q = 0; q < d.caps.nseq && S.err == kWinOk; ++q) {
@@ -818,7 +818,7 @@ poa_window_kernel(const WinParams P) {
           if (tid == 0) { tk.result[0] = 0; tk.result[1] = INT32_MIN; }
           compute_bands2<T>(x, tk, s, lb, have_lb, m.band, m.coff, &s_need2);
           if (s_need2 > tk.codes_cap) { v2_overflow = true; break; }
-          dp2_align<T>(tk, s, P.tabs, P.ring_rows, smem_raw, m.band, m.coff, &s_eval);
+          dp2_align<T>(tk, s, P.tabs, P.ring_rows, smem_raw, m.band, m.coff, s_eval);
           const int32_t found_row = tk.result[0], found = tk.result[1];
           if (!have_lb || (found_row > 0 && found >= lb)) break;
           if (tid == 0) s_retries += 1;
@@ -941,7 +941,8 @@ poa_window_kernel(const WinParams P) {
       r.n_align = s_nalign; r.retries = s_retries;
       r.nodes = S.nv; r.edges = S.ne;
       r.cells = s_cells; r.rows = s_rows; r.exported = s_exported; r.need_bytes = s_need;
-      r.eval_cells = 8ull * s_eval;
+      r.eval_cells = 8ull * s_eval[0];
+      for (int k = 0; k < 4; ++k) r.warp_cyc[k] = s_eval[1 + k];
       r.read_bases = s_bases; r.path_steps = s_steps; r.pred_entries = s_preds;
       cyc[5] += static_cast<unsigned long long>(clock64() - t5);
       for (int k = 0; k < 8; ++k) r.cyc[k] = cyc[k];

@@ -213,6 +213,7 @@ int collect_round(svs_poa_result* r, std::vector<int>* again) {
       r->res[g].rows += prev.rows; r->res[g].exported += prev.exported;
       r->res[g].read_bases += prev.read_bases; r->res[g].path_steps += prev.path_steps; r->res[g].pred_entries += prev.pred_entries;
       for (int c = 0; c < 8; ++c) r->res[g].cyc[c] += prev.cyc[c];
+      for (int c = 0; c < 4; ++c) r->res[g].warp_cyc[c] += prev.warp_cyc[c];
     }
     switch (w.status) {
       case kWinNodeCap: case kWinEdgeCap: case kWinStackCap: case kWinCodesCap: case kWinOutCap:
@@ -347,6 +348,7 @@ int wait(svs_poa_result* r) {
     st[11] += static_cast<double>(w.rows);
     st[23] += w.retries;
     for (int c = 0; c < 8; ++c) st[24 + c] += static_cast<double>(w.cyc[c]);
+    for (int c = 0; c < 4; ++c) st[33 + c] += static_cast<double>(w.warp_cyc[c]);
     if (w.status != kWinOk) st[32] += 1;
   }
   st[2] = r->kernel_ms;

@@ -28,6 +28,8 @@ struct WinResult {
   uint64_t rows, exported;  // DP rows / rows exported to global memory, summed over the alignments
   uint64_t need_bytes;      // kWinCodesCap: bytes of traceback codes the failing alignment needed
   uint64_t read_bases, path_steps, pred_entries;   // summed over the alignments (algorithmic bytes)
+  uint64_t warp_cyc[4];     // DP, summed over warps: cycles in the row loop, polling the left warp, polling the
+                            // right warp / strip boundary, waiting for the last warp at the end
   uint64_t cyc[8];          // SM cycles of thread 0 per phase: export, bands+DP, traceback, merge, rank order, finish
 };
 

@@ -11,7 +11,7 @@ from ._lib import Context, ReadSet, SvsError, c_vp, load, ptr
 STAT_NAMES = ["cells", "alignments", "dp_ms", "tb_ms", "wall_ms", "dp_launches", "tb_launches",
               "h2d_bytes", "d2h_bytes", "algo_bytes", "exported_rows", "rows", "eval_cells", "r13", "r14", "r15", "r16", "r17",
               "r18", "r19", "r20", "r21", "r22", "prune_retries", "cyc_export", "cyc_dp", "cyc_traceback", "cyc_merge",
-              "cyc_rank", "cyc_finish", "r30", "r31", "failed_groups"]
+              "cyc_rank", "cyc_finish", "r30", "r31", "failed_groups", "wcyc_loop", "wcyc_wait_left", "wcyc_wait_right", "wcyc_wait_end"]
 N_STATS = len(STAT_NAMES)
 STATUS_TEXT = {1: "graph nodes exceed the largest memory tier", 2: "graph edges exceed the largest memory tier",
                3: "aligned group of more than 8 distinct letters", 4: "rank-order stack exceeds the memory tier",
