@@ -12,7 +12,8 @@ ctx = _lib.Context(0)
 if os.environ.get("ARENA_MB"):
     ctx.set_option("arena_mb", int(os.environ["ARENA_MB"]))
 if body:
-    wins = [synth.make_sv_window(100 + i, int(body), "DEL" if i % 2 else "INS", 300, 30, 30, 12, 0.05) for i in range(nwin)]
+    depth = int(os.environ.get("DEPTH", 30))
+    wins = [synth.make_sv_window(100 + i, int(body), "DEL" if i % 2 else "INS", 300, depth, depth, max(3, depth // 3), 0.05) for i in range(nwin)]
 else:
     wins = synth.make_c2(nwin)
 seqs, groups = [], []

@@ -723,6 +723,11 @@ poa_window_kernel(const WinParams P) {
   __shared__ int32_t sweep_ring[256];
   CtaExec x{warp_tot, sweep_ring};
   const int tid = threadIdx.x;
+  if (P.sm_limit > 0) {   // profiling aid: full per-SM occupancy on a few SMs only (small arena, short ncu replays)
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (smid >= static_cast<unsigned>(P.sm_limit)) return;
+  }
   // scratch slot: any free one (at most n_slots CTAs of this kernel are resident at a time)
   if (tid == 0) {
     int k = static_cast<int>((blockIdx.x * 7919u) % static_cast<unsigned>(P.n_slots));

@@ -68,7 +68,10 @@ int window_cps(svs_ctx* ctx) { return poa_window_ctas_per_sm(ctx->poa_threads, c
 std::vector<Tier> make_tiers(svs_ctx* ctx) {
   std::vector<Tier> t;
   const int cps = std::max(1, window_cps(ctx));
-  const int sm = std::max(1, ctx->sm_count);
+  int sm = std::max(1, ctx->sm_count);
+  if (const char* sl = getenv("SVS_SM_LIMIT")) {   // profiling aid: slots for the SMs that take work only
+    if (atoi(sl) > 0) sm = std::min(sm, atoi(sl));
+  }
   for (int n : {sm * cps, sm, std::max(1, sm / 4), 8, 2, 1}) {
     if (!t.empty() && n >= t.back().n_slots) continue;
     t.push_back(Tier{n, (ctx->arena_bytes / static_cast<size_t>(n)) / 4096 * 4096});
@@ -178,7 +181,11 @@ int launch_round(svs_poa_result* r, const std::vector<int>& groups, int tier_idx
   p.prune_margin = 0.10f;
   p.dp_version = ctx->dp_kernel;
   if (const char* pm = getenv("SVS_PRUNE_MARGIN")) p.prune_margin = static_cast<float>(atof(pm));
-  const int grid = std::min(n, tier.n_slots);
+  int grid = std::min(n, tier.n_slots);
+  if (const char* sl = getenv("SVS_SM_LIMIT")) {   // profiling aid (scripts/ncu_dp.sh): see WinParams::sm_limit
+    p.sm_limit = atoi(sl);
+    if (p.sm_limit > 0) grid = std::max(1, ctx->sm_count) * std::max(1, window_cps(ctx));
+  }
   SVS_CUDA(ctx, cudaEventRecord(r->ev0, st));
   SVS_CUDA(ctx, poa_window_launch(p, grid, ctx->poa_threads, ctx->poa_cols, st));
   SVS_CUDA(ctx, cudaEventRecord(r->ev1, st));

@@ -57,6 +57,7 @@ struct WinParams {
   int prune;
   int want_msa;
   float prune_margin;
+  int sm_limit;               // profiling aid: > 0 = only CTAs that land on SMs below this id take work
   int dp_version;             // 2: warp-pipelined DP (8 columns per thread), 1: barrier-per-row DP
 };
 
