@@ -31,7 +31,7 @@ __host__ __device__ inline size_t dp2_smem_bytes(int threads, int ring_rows) {
   const int nw = threads / 32;
   return static_cast<size_t>(threads) * 8 * 4 * ring_rows   // packed-row rings
          + static_cast<size_t>(nw) * kCarryDepth * sizeof(Carry)
-         + 64                                                   // prog[]
+         + 128                                                  // prog[], fprog[]
          + static_cast<size_t>(nw) * kStageCap * 12;            // staged predecessor entries
 }
 
@@ -97,7 +97,11 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
   int32_t* ring = reinterpret_cast<int32_t*>(smem_raw) + static_cast<size_t>(warp) * ring_rows * 256;
   Carry* carry_all = reinterpret_cast<Carry*>(smem_raw + static_cast<size_t>(T) * 32 * ring_rows);
   volatile int* prog = reinterpret_cast<volatile int*>(carry_all + NW * kCarryDepth);
-  int32_t* stage = reinterpret_cast<int32_t*>(const_cast<int*>(prog) + 16) + warp * (kStageCap * 3);
+  // fprog[w]: rows of warp w whose GLOBAL stores (exported rows, strip boundary) are fenced; a fence
+  // waits for every outstanding store of the warp (the traceback codes too), so it is issued every 8
+  // rows, not per row: the per-row hand-over between neighbouring warps is shared memory only
+  volatile int* fprog = prog + 16;
+  int32_t* stage = reinterpret_cast<int32_t*>(const_cast<int*>(prog) + 32) + warp * (kStageCap * 3);
   int32_t* psrc = stage;                                        // source of the predecessor row
   uint32_t* pchk = reinterpret_cast<uint32_t*>(stage + kStageCap);   // its chunk range, lo | hi << 16
   int32_t* pbh = stage + 2 * kStageCap;                         // warp 0: H of the predecessor left of the strip
@@ -114,8 +118,10 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
   // (warp 0 starts strip p + 1 while the other warps are still in strip p); the strip boundary
   // travels through global memory (bnd), guarded by the progress of the warp that owns the last
   // chunk of the strip
-  if (lane == 0) prog[warp] = 0;
+  if (lane == 0) { prog[warp] = 0; fprog[warp] = 0; }
   __syncthreads();
+  int next_fence = 0;
+  bool unfenced = false;   // rows processed since my last fence
   const int wlast = static_cast<int>(((tk.strip >> 3) - 1) >> 5);   // warp that owns the last chunk of a full strip
   long long t_wait_left = 0, t_wait_flow = 0, t_wait_bnd = 0;   // cycles lane 0 spent polling (per warp)
   const long long t_begin = clock64();
@@ -176,7 +182,8 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
       const bool m_inter = mine && m_lo <= m_hi && m_chi >= wc0 && m_clo <= wc1;
       const unsigned any = __ballot_sync(0xffffffffu, m_inter);
       if (any == 0) {   // no row of the batch has a cell in my 256 columns
-        if (lane == 31) prog[warp] = pbase_prog + static_cast<int>(i0 + nrows - 1);
+        if (unfenced) { __threadfence_block(); unfenced = false; }
+        if (lane == 31) { prog[warp] = pbase_prog + static_cast<int>(i0 + nrows - 1); fprog[warp] = pbase_prog + static_cast<int>(i0 + nrows - 1); }
         i0 += nrows;
         continue;
       }
@@ -184,9 +191,9 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
       // previous strip left behind if the band covered its last chunk
       if (warp == 0 && pass > 0) {   // the previous strip must have passed the rows of this batch
         const int need = static_cast<int>((pass - 1) * (R + 1) + i0 + nrows - 1);
-        if (lane == 0) { const long long t0 = clock64(); while (ld_prog(prog + wlast) < need) { } t_wait_bnd += clock64() - t0; }
+        if (lane == 0) { const long long t0 = clock64(); while (ld_prog(fprog + wlast) < need) { } t_wait_bnd += clock64() - t0; }
         __syncwarp();
-        __threadfence_block();
+        asm volatile("" ::: "memory");
       }
       if (warp == 0 && mine) {
         if (pass == 0) {
@@ -255,7 +262,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
         } else if (need_left) {   // predecessor rows left of my span: the left warp must have done row i - 1
           if (lane == 0) { const long long t0 = clock64(); while (ld_prog(prog + warp - 1) < pbase_prog + static_cast<int>(i) - 1) { } t_wait_left += clock64() - t0; }
           __syncwarp();
-          __threadfence_block();
+          asm volatile("" ::: "memory");
         }
         const int abs_i = pbase_prog + static_cast<int>(i);   // carry-ring slots are indexed by absolute progress
         if (NW > 1 && warp + 1 < NW && abs_i >= next_check) {
@@ -301,7 +308,12 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
 #pragma unroll
                 for (int c = 0; c < kC; ++c) w[c] = NEGW;
               }
-              if (warp > 0 && left_ok) hl_warp_edge = unpack_h(__ldcg(row + j0 - 1));
+              if (warp > 0 && __shfl_sync(0xffffffffu, static_cast<int>(left_ok), 0)) {
+                // lane 0's left column was written by the left warp at least ring_rows rows ago: wait for its fence
+                if (lane == 0) { const long long t0 = clock64(); while (ld_prog(fprog + warp - 1) < pbase_prog + pbh[e]) { } t_wait_left += clock64() - t0; }
+                __syncwarp();
+                if (left_ok) hl_warp_edge = unpack_h(__ldcg(row + j0 - 1));
+              }
               hl = (lane == 0) ? hl_warp_edge : ((left_ok && active) ? unpack_h(__ldcg(row + j0 - 1)) : kNegBand);
             } else {
               const int32_t* row = ring + static_cast<size_t>(src) * 256;
@@ -353,7 +365,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
         if (warp > 0 && need_left) {   // the scan needs the left warp's state of THIS row
           if (lane == 0) { const long long t0 = clock64(); while (ld_prog(prog + warp - 1) < pbase_prog + static_cast<int>(i)) { } t_wait_left += clock64() - t0; }
           __syncwarp();
-          __threadfence_block();
+          asm volatile("" ::: "memory");
           if (clo < wc0) cin = carry_left[abs_i & (kCarryDepth - 1)];
         }
         int32_t ein0 = 0, qin0 = 0;
@@ -394,14 +406,19 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
           bout[2 * bstride + i] = se;
           bout[3 * bstride + i] = sq;
         }
-        if (warp == wlast) __syncwarp();
+        if (abs_i >= next_fence) {   // rows < i (and the boundary of row i) are now visible to the whole CTA
+          __threadfence_block();
+          if (lane == 31) fprog[warp] = abs_i - 1;
+          next_fence = abs_i + 8;
+        }
+        unfenced = true;
         if (lane == 31) {
           if (warp + 1 < NW) {
             Carry out;
             out.A = a7; out.E = se; out.Q = sq; out.H = imax(a7, imax(se, sq));
             carry_mine[abs_i & (kCarryDepth - 1)] = out;
           }
-          __threadfence_block();
+          asm volatile("" ::: "memory");   // same-thread shared-memory stores are performed in order
           prog[warp] = abs_i;
         }
 
@@ -459,6 +476,10 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
         }
       }
       // rows at the end of the batch that were skipped: tell the consumer
+      if (i0 + nrows > R) {   // end of the pass: everything is stored
+        if (unfenced) { __threadfence_block(); unfenced = false; }
+        if (lane == 31) fprog[warp] = pbase_prog + static_cast<int>(R);
+      }
       if (lane == 31) prog[warp] = pbase_prog + static_cast<int>(i0 + nrows - 1);
       i0 += nrows;
     }
