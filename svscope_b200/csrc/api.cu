@@ -114,13 +114,13 @@ int svs_set_option(svs_ctx* ctx, const char* key, int64_t value) {
   } else if (k == "prune") {
     ctx->prune = value != 0;
   } else if (k == "poa_cols") {
-    if (value != 4 && value != 8 && value != 16) return fail(ctx, SVS_ERR_ARG, "poa_cols must be 4, 8 or 16");
+    if (value != 8) return fail(ctx, SVS_ERR_ARG, "poa_cols must be 8");
     ctx->poa_cols = static_cast<int>(value);
   } else if (k == "ring_rows") {
     if (value < 1 || value > 64) return fail(ctx, SVS_ERR_ARG, "ring_rows out of range");
     ctx->ring_rows = static_cast<int>(value);
   } else if (k == "dp_kernel") {
-    if (value != 1 && value != 2) return fail(ctx, SVS_ERR_ARG, "dp_kernel must be 1 or 2");
+    if (value != 2) return fail(ctx, SVS_ERR_ARG, "dp_kernel must be 2 (the barrier-per-row kernel is gone)");
     ctx->dp_kernel = static_cast<int>(value);
   } else if (k == "workers") {
     if (value < 1 || value > 64) return fail(ctx, SVS_ERR_ARG, "workers out of range");

@@ -17,7 +17,7 @@ struct svs_ctx {
   int poa_threads = 128;   // 128 threads x 8 columns: four resident windows per SM
   int prune = 1;       // exact score-bound pruning of DP cells (persistent kernel)
   int poa_cols = 8;    // read columns per thread (16 only with 256 threads)
-  int ring_rows = 10;
+  int ring_rows = 8;
   int dp_kernel = 2;   // 2: warp-pipelined DP (no CTA barrier per row), 1: barrier-per-row DP
   int workers = 4;
   int64_t arena_mb = 0;

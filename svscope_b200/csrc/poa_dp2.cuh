@@ -29,7 +29,7 @@ struct __align__(16) Carry {
 
 __host__ __device__ inline size_t dp2_smem_bytes(int threads, int ring_rows) {
   const int nw = threads / 32;
-  return static_cast<size_t>(threads) * 8 * 4 * ring_rows   // packed-row rings
+  return static_cast<size_t>(threads) * 8 * 4 * (ring_rows + 2)   // packed-row rings + the source row + a scratch row
          + static_cast<size_t>(nw) * kCarryDepth * sizeof(Carry)
          + 128                                                  // prog[], fprog[]
          + static_cast<size_t>(nw) * kStageCap * 12;            // staged predecessor entries
@@ -86,6 +86,35 @@ __device__ void compute_bands2(CtaExec& x, const PoaTask& tk, const Scores& s, i
 
 __device__ __forceinline__ int ld_prog(const volatile int* p) { return *p; }
 
+// Rare path of the predecessor fold: the row lives in global memory (it has a successor more than
+// ring_rows rows away).  Copies my chunk into the warp's scratch row in shared memory, so that the
+// fold itself has a single source, and returns lane 0's left neighbour.  Called by the whole warp.
+__device__ __noinline__ int32_t dp2_stage_global(const PoaTask& tk, int32_t xslot, uint32_t j0, bool load_chunk, bool left_ok,
+                                                 bool warp0, int32_t bh, const volatile int* fprog_left, int pbase_prog,
+                                                 int32_t* scratch, long long* t_wait) {
+  const int lane = threadIdx.x & 31;
+  const int32_t* row = tk.xrows + static_cast<uint64_t>(xslot) * tk.ldx + 3;
+  __syncwarp();   // the previous user of the scratch row is done
+  if (load_chunk) {
+    const int4 v0 = __ldcg(reinterpret_cast<const int4*>(row + j0));
+    const int4 v1 = __ldcg(reinterpret_cast<const int4*>(row + j0 + 4));
+    *reinterpret_cast<int4*>(scratch + 8 * lane) = v0;
+    *reinterpret_cast<int4*>(scratch + 8 * lane + 4) = v1;
+  }
+  int32_t hl0 = warp0 ? bh : kNegBand;
+  if (!warp0 && __shfl_sync(0xffffffffu, static_cast<int>(left_ok), 0)) {
+    // lane 0's left column was written by the left warp at least ring_rows rows ago: wait for its fence
+    if (lane == 0) {
+      const long long t0 = clock64();
+      while (*fprog_left < pbase_prog + bh) { }
+      *t_wait += clock64() - t0;
+      hl0 = unpack_h(__ldcg(row + j0 - 1));
+    }
+  }
+  __syncwarp();
+  return hl0;
+}
+
 template <int T>
 __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, const SingleTables& tabs, const int ring_rows,
                                           unsigned char* smem_raw, const int32_t* __restrict__ band,
@@ -94,8 +123,11 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
   constexpr int NW = T / 32;
   const int32_t NEGW = pack_cell(kNegBand, kNeg, kNeg);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int32_t* ring = reinterpret_cast<int32_t*>(smem_raw) + static_cast<size_t>(warp) * ring_rows * 256;
-  Carry* carry_all = reinterpret_cast<Carry*>(smem_raw + static_cast<size_t>(T) * 32 * ring_rows);
+  // per warp: ring_rows packed rows (row r in slot r % ring_rows), slot ring_rows = the virtual source row
+  // in my columns, slot ring_rows + 1 = scratch for a predecessor row fetched from global memory: every
+  // predecessor is read from shared memory by ONE copy of the cell code
+  int32_t* ring = reinterpret_cast<int32_t*>(smem_raw) + static_cast<size_t>(warp) * (ring_rows + 2) * 256;
+  Carry* carry_all = reinterpret_cast<Carry*>(smem_raw + static_cast<size_t>(T) * 32 * (ring_rows + 2));
   volatile int* prog = reinterpret_cast<volatile int*>(carry_all + NW * kCarryDepth);
   // fprog[w]: rows of warp w whose GLOBAL stores (exported rows, strip boundary) are fenced; a fence
   // waits for every outstanding store of the warp (the traceback codes too), so it is issued every 8
@@ -150,10 +182,13 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
       const uint32_t j = j0 + c;
       rd[c] = (active && j <= L) ? static_cast<int32_t>(tk.read[j - 1]) : 0x100;
     }
-    int32_t wprev[kC];
+    {   // the virtual source row in my columns (H of a leading gap; F, O = -inf)
+      int32_t* r0 = ring + static_cast<size_t>(ring_rows) * 256 + kC * lane;
 #pragma unroll
-    for (int c = 0; c < kC; ++c) wprev[c] = NEGW;
-    int32_t hleft_adj = kNegBand;   // H[i-1][j0-1]
+      for (int c = 0; c < kC; ++c) r0[c] = pack_cell(row0_h(s, static_cast<int32_t>(j0) + c), kNeg, kNeg);
+      __syncwarp();
+    }
+    const int32_t h_row0_left = row0_h(s, static_cast<int32_t>(jb + 256u * warp) - 1);   // source row, column left of my warp
 
     uint32_t i0 = 1;
     while (i0 <= R) {
@@ -213,14 +248,14 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
           int32_t src, bh = kNegBand;
           uint32_t chk;
           if (p == 0) {
-            src = kSrcRow0;
+            src = ring_rows;          // the source-row slot
             chk = 0xffff0000u;
+            bh = h_row0_left;
           } else {
             const int2 pb = *reinterpret_cast<const int2*>(band + 2 * p);
             const int32_t pclo = (pb.x - 1) >> 3, pchi = (pb.y - 1) >> 3;
             chk = pb.x <= pb.y ? (static_cast<uint32_t>(pclo) | (static_cast<uint32_t>(pchi) << 16)) : 1u;   // 1: lo = 1 > hi = 0
-            if (p + 1 == mi) src = kSrcAdj;
-            else if (mi - p <= static_cast<uint32_t>(ring_rows)) src = static_cast<int32_t>(p % ring_rows);
+            if (mi - p <= static_cast<uint32_t>(ring_rows)) src = static_cast<int32_t>(p % ring_rows);
             else src = kSrcGlobal | tk.xslot[p];
             if (warp == 0) {
               if (pass == 0) bh = tk.h0[p];
@@ -251,6 +286,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
         const uint32_t rflags = info >> 8;
         const bool single = (ne - nb == 1);
         const bool t_active = active && gc >= clo && gc <= chi;
+        __syncwarp();   // the packed row my neighbours stored last is visible
 
         // ---- pipeline control -----------------------------------------------------------------
         Carry cin;
@@ -281,56 +317,30 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
           const int32_t pclo = static_cast<int32_t>(chk & 0xffffu), pchi = static_cast<int32_t>(chk >> 16);
           const bool chunk_ok = gc >= pclo && gc <= pchi;
           const bool left_ok = gc - 1 >= pclo && gc - 1 <= pchi;
-          int32_t w[kC];
-          int32_t hl;
-          if (src == kSrcRow0) {
-#pragma unroll
-            for (int c = 0; c < kC; ++c) w[c] = pack_cell(row0_h(s, static_cast<int32_t>(j0) + c), kNeg, kNeg);
-            hl = row0_h(s, static_cast<int32_t>(j0) - 1);
+          int32_t hl0;   // lane 0: H of the predecessor row in the column left of my warp (or of the strip)
+          const int32_t* row;
+          if (src & kSrcGlobal) {   // rare: a row with a far successor, kept in global memory
+            hl0 = dp2_stage_global(tk, src & ~kSrcGlobal, j0, chunk_ok && active, left_ok, warp == 0, pbh[e],
+                                   fprog + (warp > 0 ? warp - 1 : 0), pbase_prog, ring + static_cast<size_t>(ring_rows + 1) * 256,
+                                   &t_wait_left);
+            row = ring + static_cast<size_t>(ring_rows + 1) * 256;
           } else {
-            // H of the predecessor row in the column left of my chunk
-            int32_t hl_warp_edge = kNegBand;   // lane 0: the column belongs to the warp on my left (or the strip boundary)
-            if (warp == 0) hl_warp_edge = pbh[e];
-            if (src == kSrcAdj) {
-#pragma unroll
-              for (int c = 0; c < kC; ++c) w[c] = chunk_ok ? wprev[c] : NEGW;
-              if (warp > 0 && left_ok) hl_warp_edge = carry_left[(abs_i - 1) & (kCarryDepth - 1)].H;
-              hl = (lane == 0) ? hl_warp_edge : (left_ok ? hleft_adj : kNegBand);
-            } else if (src & kSrcGlobal) {
-              const int32_t* row = tk.xrows + static_cast<uint64_t>(src & ~kSrcGlobal) * tk.ldx + 3;
-              if (chunk_ok && active) {
-#pragma unroll
-                for (int q = 0; q < kC / 4; ++q) {
-                  const int4 v = __ldcg(reinterpret_cast<const int4*>(row + j0 + 4 * q));
-                  w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-                }
-              } else {
-#pragma unroll
-                for (int c = 0; c < kC; ++c) w[c] = NEGW;
-              }
-              if (warp > 0 && __shfl_sync(0xffffffffu, static_cast<int>(left_ok), 0)) {
-                // lane 0's left column was written by the left warp at least ring_rows rows ago: wait for its fence
-                if (lane == 0) { const long long t0 = clock64(); while (ld_prog(fprog + warp - 1) < pbase_prog + pbh[e]) { } t_wait_left += clock64() - t0; }
-                __syncwarp();
-                if (left_ok) hl_warp_edge = unpack_h(__ldcg(row + j0 - 1));
-              }
-              hl = (lane == 0) ? hl_warp_edge : ((left_ok && active) ? unpack_h(__ldcg(row + j0 - 1)) : kNegBand);
-            } else {
-              const int32_t* row = ring + static_cast<size_t>(src) * 256;
-              if (chunk_ok) {
-#pragma unroll
-                for (int q = 0; q < kC / 4; ++q) {
-                  const int4 v = *reinterpret_cast<const int4*>(row + kC * lane + 4 * q);
-                  w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-                }
-              } else {
-#pragma unroll
-                for (int c = 0; c < kC; ++c) w[c] = NEGW;
-              }
-              if (warp > 0 && left_ok) hl_warp_edge = carry_left[static_cast<uint32_t>(pbase_prog + pbh[e]) & (kCarryDepth - 1)].H;
-              hl = (lane == 0) ? hl_warp_edge : (left_ok ? unpack_h(row[kC * lane - 1]) : kNegBand);
-            }
+            row = ring + static_cast<size_t>(src) * 256;
+            const int32_t bh = pbh[e];
+            hl0 = (warp == 0 || src == ring_rows) ? bh
+                                                   : (left_ok ? carry_left[static_cast<uint32_t>(pbase_prog + bh) & (kCarryDepth - 1)].H : kNegBand);
           }
+          int32_t w[kC];
+          {
+            const int4 v0 = *reinterpret_cast<const int4*>(row + kC * lane);
+            const int4 v1 = *reinterpret_cast<const int4*>(row + kC * lane + 4);
+            w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+          }
+          if (!chunk_ok) {
+#pragma unroll
+            for (int c = 0; c < kC; ++c) w[c] = NEGW;
+          }
+          int32_t hl = (lane == 0) ? hl0 : (left_ok ? unpack_h(row[kC * lane - 1]) : kNegBand);
           if (t_active) {
             if (single) {
 #pragma unroll
@@ -396,7 +406,6 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
         cy.Q = __shfl_up_sync(0xffffffffu, sq, 1);
         if (lane == 0) { cy.A = cin.A; cy.E = cin.E; cy.Q = cin.Q; }
         cy.H = imax(cy.A, imax(cy.E, cy.Q));
-        hleft_adj = cy.H;
 
         // ---- publish the state of my warp's last column (or of the strip's last column, through
         //      global memory, for the next strip), then the row index ---------------------------------
@@ -426,6 +435,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
         if (t_active) {
           ++n_chunks;
           uint32_t cw[kC / 2];
+          int32_t wp[kC];
           int32_t hsel = INT32_MIN;
           if (single) {
 #pragma unroll
@@ -433,7 +443,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
               int32_t H;
               const uint32_t cd = cell_finish_single(acc[c], cy, s, H);
               H = imax(H, kNegBand); cy.H = H; cy.A = imax(cy.A, kNegBand);   // pruned neighbours must not drift
-              wprev[c] = pack_cell(H, acc[c].Fm, acc[c].Om);
+              wp[c] = pack_cell(H, acc[c].Fm, acc[c].Om);
               if (c & 1) cw[c >> 1] |= cd << 16; else cw[c >> 1] = cd;
               if (c == c_end) hsel = H;
             }
@@ -443,7 +453,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
               int32_t H, Fv, Ov;
               const uint32_t cd = cell_finish_key(acc[c], cy, s, H, Fv, Ov);
               H = imax(H, kNegBand); cy.H = H; cy.A = imax(cy.A, kNegBand);
-              wprev[c] = pack_cell(H, Fv, Ov);
+              wp[c] = pack_cell(H, Fv, Ov);
               if (c & 1) cw[c >> 1] |= cd << 16; else cw[c >> 1] = cd;
               if (c == c_end) hsel = H;
             }
@@ -458,21 +468,18 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
             *reinterpret_cast<uint4*>(crow + 16ull * cidx) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
           }
           int32_t* rrow = ring + static_cast<size_t>(i % ring_rows) * 256 + kC * lane;
-          *reinterpret_cast<int4*>(rrow) = make_int4(wprev[0], wprev[1], wprev[2], wprev[3]);
-          *reinterpret_cast<int4*>(rrow + 4) = make_int4(wprev[4], wprev[5], wprev[6], wprev[7]);
+          *reinterpret_cast<int4*>(rrow) = make_int4(wp[0], wp[1], wp[2], wp[3]);
+          *reinterpret_cast<int4*>(rrow + 4) = make_int4(wp[4], wp[5], wp[6], wp[7]);
           if (rflags & kFlagExport) {
             int32_t* xrow = tk.xrows + static_cast<uint64_t>(tk.xslot[i]) * tk.ldx + 3;
-            *reinterpret_cast<int4*>(xrow + j0) = make_int4(wprev[0], wprev[1], wprev[2], wprev[3]);
-            *reinterpret_cast<int4*>(xrow + j0 + 4) = make_int4(wprev[4], wprev[5], wprev[6], wprev[7]);
+            *reinterpret_cast<int4*>(xrow + j0) = make_int4(wp[0], wp[1], wp[2], wp[3]);
+            *reinterpret_cast<int4*>(xrow + j0 + 4) = make_int4(wp[4], wp[5], wp[6], wp[7]);
             if (tid == 0 && pass == 0) xrow[0] = pack_cell(cin.A, kNeg, kNeg);
           }
           if (owns_end && (rflags & kFlagSink) && hsel > best) {
             best = hsel;
             best_row = i;
           }
-        } else {
-#pragma unroll
-          for (int c = 0; c < kC; ++c) wprev[c] = NEGW;   // this row has no cell in my chunk
         }
       }
       // rows at the end of the batch that were skipped: tell the consumer

@@ -41,16 +41,14 @@ def _random_group(rng, it, lmax=400):
     return seqs
 
 
-@pytest.mark.parametrize("threads,ring,cols,dp", [(128, 10, 8, 2), (512, 8, 8, 2), (256, 12, 16, 1), (256, 12, 8, 2),
-                                                  (128, 1, 8, 2), (512, 3, 8, 2), (128, 24, 8, 2), (256, 2, 16, 1),
-                                                  (512, 24, 4, 1), (512, 5, 4, 1), (128, 10, 8, 1), (256, 3, 8, 1),
-                                                  (128, 2, 8, 2), (256, 5, 8, 2)])
+@pytest.mark.parametrize("threads,ring,cols,dp", [(128, 8, 8, 2), (512, 8, 8, 2), (256, 10, 8, 2), (128, 1, 8, 2),
+                                                  (512, 3, 8, 2), (128, 24, 8, 2), (128, 2, 8, 2), (256, 5, 8, 2),
+                                                  (256, 1, 8, 2), (512, 1, 8, 2)])
 def test_alignment_pairs_bit_exact(ctx, oracle, threads, ring, cols, dp):
     """Every alignment (node id, read position) list equals the oracle's, for several CTA
     sizes and ring depths (ring 1 forces almost every non-adjacent predecessor through the
     exported rows in global memory).  All shapes run the window kernel (graph resident on the
-    device); the default is 128 x 8 with a ring of 10 rows (four resident windows per SM) and the
-    warp-pipelined dynamic programme (dp 2); dp 1 is the barrier-per-row one."""
+    device); the default is 128 threads x 8 columns with a ring of 8 rows (four resident windows per SM)."""
     from svscope_b200.poa_api import align_pairs
     ctx.set_option("poa_threads", threads)
     ctx.set_option("ring_rows", ring)
@@ -68,7 +66,7 @@ def test_alignment_pairs_bit_exact(ctx, oracle, threads, ring, cols, dp):
             o.close()
     finally:
         ctx.set_option("poa_threads", 128)
-        ctx.set_option("ring_rows", 10)
+        ctx.set_option("ring_rows", 8)
         ctx.set_option("poa_cols", 8)
         ctx.set_option("dp_kernel", 2)
 
