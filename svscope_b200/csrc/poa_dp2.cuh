@@ -308,13 +308,13 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
           cin.E = __shfl_sync(0xffffffffu, m_bE, r);
           cin.Q = __shfl_sync(0xffffffffu, m_bQ, r);
         } else if (need_left) {   // predecessor rows left of my span: the left warp must have done row i - 1
-          if (lane == 0) { const long long t0 = clock64(); while (ld_prog(prog + warp - 1) < pbase_prog + static_cast<int>(i) - 1) { } t_wait_left += clock64() - t0; }
+          if (lane == 0) { while (ld_prog(prog + warp - 1) < pbase_prog + static_cast<int>(i) - 1) { } }
           __syncwarp();
           asm volatile("" ::: "memory");
         }
         const int abs_i = pbase_prog + static_cast<int>(i);   // carry-ring slots are indexed by absolute progress
         if (NW > 1 && warp + 1 < NW && abs_i >= next_check) {
-          if (lane == 0) { const long long t0 = clock64(); while (ld_prog(prog + warp + 1) < abs_i - 32) { } t_wait_left += clock64() - t0; }
+          if (lane == 0) { while (ld_prog(prog + warp + 1) < abs_i - 32) { } }
           __syncwarp();
           next_check = abs_i + 8;
         }
@@ -439,35 +439,36 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
         // ---- phase 2: H, traceback codes, packed row ---------------------------------------------
         if (t_active) {
           ++n_chunks;
-          uint32_t cw[kC / 2];
-          int32_t wp[kC];
           int32_t hsel = INT32_MIN;
-#pragma unroll
-          for (int c = 0; c < kC; ++c) {
-            int32_t H, Fv, Ov;
-            const uint32_t cd = cell_finish_key(acc[c], cy, s, H, Fv, Ov);
-            H = imax(H, kNegBand); cy.H = H; cy.A = imax(cy.A, kNegBand);   // pruned neighbours must not drift
-            wp[c] = pack_cell(H, Fv, Ov);
-            if (c & 1) cw[c >> 1] |= cd << 16; else cw[c >> 1] = cd;
-            if (c == c_end) hsel = H;
-          }
           uint8_t* crow = tk.codes + 8ull * row_coff;
           const uint32_t cidx = static_cast<uint32_t>(gc - clo);
-          if (single) {   // low bytes only
-            const uint32_t b0 = (cw[0] & 0xffu) | ((cw[0] >> 8) & 0xff00u) | ((cw[1] & 0xffu) << 16) | ((cw[1] & 0xff0000u) << 8);
-            const uint32_t b1 = (cw[2] & 0xffu) | ((cw[2] >> 8) & 0xff00u) | ((cw[3] & 0xffu) << 16) | ((cw[3] & 0xff0000u) << 8);
-            *reinterpret_cast<uint2*>(crow + 8ull * cidx) = make_uint2(b0, b1);
-          } else {
-            *reinterpret_cast<uint4*>(crow + 16ull * cidx) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
-          }
           int32_t* rrow = ring + static_cast<size_t>(i % ring_rows) * 256 + kC * lane;
-          *reinterpret_cast<int4*>(rrow) = make_int4(wp[0], wp[1], wp[2], wp[3]);
-          *reinterpret_cast<int4*>(rrow + 4) = make_int4(wp[4], wp[5], wp[6], wp[7]);
-          if (rflags & kFlagExport) {
-            int32_t* xrow = tk.xrows + static_cast<uint64_t>(tk.xslot[i]) * tk.ldx + 3;
-            *reinterpret_cast<int4*>(xrow + j0) = make_int4(wp[0], wp[1], wp[2], wp[3]);
-            *reinterpret_cast<int4*>(xrow + j0 + 4) = make_int4(wp[4], wp[5], wp[6], wp[7]);
-            if (tid == 0 && pass == 0) xrow[0] = pack_cell(cin.A, kNeg, kNeg);
+          int32_t* xrow = (rflags & kFlagExport) ? tk.xrows + static_cast<uint64_t>(tk.xslot[i]) * tk.ldx + 3 + j0 : nullptr;
+          // two halves of four cells through ONE copy of the cell code (instruction-cache footprint):
+          // the second half's accumulators move into the first half's registers
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            uint32_t cw0 = 0, cw1 = 0;
+            int32_t wp[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              int32_t H, Fv, Ov;
+              const uint32_t cd = cell_finish_key(acc[c], cy, s, H, Fv, Ov);
+              H = imax(H, kNegBand); cy.H = H; cy.A = imax(cy.A, kNegBand);   // pruned neighbours must not drift
+              wp[c] = pack_cell(H, Fv, Ov);
+              if (c == 0) cw0 = cd; else if (c == 1) cw0 |= cd << 16; else if (c == 2) cw1 = cd; else cw1 |= cd << 16;
+              if (4 * h + c == c_end) hsel = H;
+            }
+            if (single) {   // low bytes only
+              const uint32_t b = (cw0 & 0xffu) | ((cw0 >> 8) & 0xff00u) | ((cw1 & 0xffu) << 16) | ((cw1 & 0xff0000u) << 8);
+              *reinterpret_cast<uint32_t*>(crow + 8ull * cidx + 4 * h) = b;
+            } else {
+              *reinterpret_cast<uint2*>(crow + 16ull * cidx + 8 * h) = make_uint2(cw0, cw1);
+            }
+            *reinterpret_cast<int4*>(rrow + 4 * h) = make_int4(wp[0], wp[1], wp[2], wp[3]);
+            if (xrow != nullptr) *reinterpret_cast<int4*>(xrow + 4 * h) = make_int4(wp[0], wp[1], wp[2], wp[3]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c] = acc[c + 4];
           }
           if (owns_end && (rflags & kFlagSink) && hsel > best) {
             best = hsel;
