@@ -109,7 +109,7 @@ int svs_set_option(svs_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return SVS_ERR_ARG;
   const std::string k(key);
   if (k == "poa_threads") {
-    if (value != 128 && value != 256 && value != 512) return fail(ctx, SVS_ERR_ARG, "poa_threads must be 128, 256 or 512");
+    if (value != 128 && value != 256 && value != 384 && value != 512) return fail(ctx, SVS_ERR_ARG, "poa_threads must be 128, 256, 384 or 512");
     ctx->poa_threads = static_cast<int>(value);
   } else if (k == "prune") {
     ctx->prune = value != 0;

@@ -406,7 +406,7 @@ int poa_dp_cols_per_pass(int threads, int) { return threads * 8; }
 size_t poa_window_smem_bytes(int threads, int ring_rows, int) { return dp2_smem_bytes(threads, ring_rows); }
 
 int poa_window_ctas_per_sm(int threads, int ring_rows, int cols) {
-  if (cols != 8 || (threads != 128 && threads != 256 && threads != 512)) return 0;
+  if (cols != 8 || (threads != 128 && threads != 256 && threads != 384 && threads != 512)) return 0;
   const size_t smem = poa_window_smem_bytes(threads, ring_rows, cols) + 2048;   // + static shared memory
   if (smem > 227 * 1024) return 0;
   const int by_smem = static_cast<int>((227 * 1024) / (smem + 1024));
@@ -424,6 +424,7 @@ cudaError_t poa_window_configure(int threads, int ring_rows, int cols) {
   const int bytes = static_cast<int>(poa_window_smem_bytes(threads, ring_rows, cols));
   if (threads == 128) return window_cfg<128>(bytes);
   if (threads == 256) return window_cfg<256>(bytes);
+  if (threads == 384) return window_cfg<384>(bytes);
   return window_cfg<512>(bytes);
 }
 
@@ -432,6 +433,7 @@ cudaError_t poa_window_launch(const WinParams& p, int grid, int threads, int col
   const size_t smem = poa_window_smem_bytes(threads, p.ring_rows, cols);
   if (threads == 128) poa_window_kernel<128, 8><<<grid, 128, smem, stream>>>(p);
   else if (threads == 256) poa_window_kernel<256, 8><<<grid, 256, smem, stream>>>(p);
+  else if (threads == 384) poa_window_kernel<384, 8><<<grid, 384, smem, stream>>>(p);
   else if (threads == 512) poa_window_kernel<512, 8><<<grid, 512, smem, stream>>>(p);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
