@@ -324,13 +324,21 @@ def upload_windows(ctx: Context, windows) -> ReadSet:
 def localgraph_batch(windows, ctx: Optional[Context] = None, reads: Optional[ReadSet] = None,
                      windowFlags: Optional[Sequence[str]] = None, Tlabel="tumor", readcutoff=3, hcutoff=3,
                      scutoff=0.05, edit_distance: bool = False, keep_aux: bool = False,
-                     reseed: bool = True) -> BatchOutput:
+                     reseed: bool = True, chunks: int = 3) -> BatchOutput:
     """``Decision`` for every window of the list; returns the 10-field records in input order.
 
     ``reads`` may be a ReadSet made by ``upload_windows`` beforehand (inputs already resident
-    in HBM); otherwise the sequences are uploaded here."""
+    in HBM); otherwise the sequences are uploaded here.
+
+    The windows are dealt (by cost) into ``chunks`` interleaved sub-batches whose device stages
+    are submitted asynchronously: the window-MSA kernel of sub-batch k+1 and the consensus
+    kernel of sub-batch k-1 run (filling each other's tails) while the host selects features
+    and drives the mixture model of sub-batch k; the edit-distance matrices run on a side
+    thread behind the first MSA kernels."""
+    import threading
+    from .poa_api import PoaJob
     ctx = ctx or Context.default()
-    tm: Dict[str, float] = {}
+    tm: Dict[str, float] = {k: 0.0 for k in ("gate", "poa_msa", "features", "mixture", "poa_consensus", "records")}
     ACCT.clear()
     t0 = time.perf_counter()
     nw = len(windows)
@@ -352,131 +360,186 @@ def localgraph_batch(windows, ctx: Optional[Context] = None, reads: Optional[Rea
         if len(seqs) > 3 and tags.shape[0] >= 2 and np.min(counts) >= 3:
             live.append(i)
     tm["gate"] = time.perf_counter() - t0
-    # ---- stage 2: window MSA ---------------------------------------------------------------
+    # the per-cluster consensus runs on the upper-cased sequences (DecisionMaker.py:157-171 decodes
+    # the encoded MSA rows, and the encoder upper-cases); the window MSA is case-sensitive
+    cons_reads, own_cons_reads = reads, False
+    if any(s != s.upper() for i in live for s in windows[i][0]):
+        cons_reads = ReadSet(ctx, [s.upper() for w in windows for s in w[0]] + [""])
+        own_cons_reads = True
+    # ---- sub-batches: largest windows first, dealt round-robin ----------------------------
+    cost = {i: sum(len(s) for s in windows[i][0]) * max(len(s) for s in windows[i][0]) for i in live}
+    order = sorted(live, key=lambda i: -cost[i])
+    nchunk = max(1, min(int(chunks), len(order) // 64 if len(order) >= 128 else 1))
+    parts = [order[k::nchunk] for k in range(nchunk)]
+    st_poa: Dict[str, float] = {}
+
+    def add_stats(st):
+        for k, v in st.items():
+            if k != "status":
+                st_poa[k] = st_poa.get(k, 0.0) + float(v)
+
+    # ---- stage 2: window MSA, all sub-batches submitted at once -------------------------------
     t1 = time.perf_counter()
-    groups = [list(range(int(base[i]), int(base[i + 1]))) for i in live]
-    _, msas, st_msa = poa_groups(ctx, reads, groups, want_msa=True, as_array=True, strict=False)
-    if st_msa["status"].any():
-        # a window the device cannot align (graph beyond the largest memory tier, more than 31
-        # in-edges at one node, ...) fails alone: flagged record, the batch goes on
-        ok = [k for k in range(len(live)) if st_msa["status"][k] == 0]
-        for k in np.flatnonzero(st_msa["status"]):
-            records[live[k]][9] = flags[live[k]] + "|GraphLimit%d" % int(st_msa["status"][k])
-        live = [live[k] for k in ok]
-        msas = [msas[k] for k in ok]
-    tm["poa_msa"] = time.perf_counter() - t1
-    # ---- stage 3: encode, margins, features ---------------------------------------------------
-    t1 = time.perf_counter()
-    encs, drops, cutoffs, id_lists, row_src = [], [], [], [], []
-    for i, msa in zip(live, msas):
-        seqs, ids, f5, f3, _ = windows[i]
-        ids = np.asarray(ids)
-        lens = np.array([len(s) for s in seqs[1:]])
-        enc = encode_msa(msa)
-        nonempty = np.flatnonzero(lens != 0)
-        if nonempty.size != lens.size:
-            # DataScanner.py:198-209: gap rows are appended once per NON-empty read and the
-            # id list becomes the non-empty ids twice (the reference's own quirk)
-            kept = list(ids[nonempty])
-            enc = np.concatenate([enc, np.full((len(kept), enc.shape[1]), 4, enc.dtype)], axis=0)
-            ids = np.array(kept + kept)
-            src = [int(base[i]) + 1 + int(r) for r in nonempty] + [empty_idx] * len(kept)
-        else:
-            src = [int(base[i]) + 1 + r for r in range(len(lens))]
-        drop = np.zeros(enc.shape[1], np.uint8)
-        drop[margin_columns(msa[0], f5, f3)] = 1
-        encs.append(enc)
-        drops.append(drop)
-        cutoffs.append(float(max([hcutoff, enc.shape[0] * scutoff])))
-        id_lists.append(ids)
-        row_src.append(src)
-    feats = msa_features(ctx, [e[1:] for e in encs], drops, cutoffs)
-    tm["features"] = time.perf_counter() - t1
-    # ---- stage 4/5: mixture model ----------------------------------------------------------
-    t1 = time.perf_counter()
-    em_idx, Xs, sims, zps = [], [], [], []
-    for k, (enc, (keep, nf, zp, ident)) in enumerate(zip(encs, feats)):
-        n = enc.shape[0] - 1
-        if n != 0 and nf >= 10:                                            # DecisionMaker.py:137
-            X = np.ascontiguousarray(enc[1:][:, keep])
-            sim = ident.astype(np.float64) / nf
-            np.fill_diagonal(sim, 1.0)
-            em_idx.append(k)
-            Xs.append(X)
-            sims.append(sim)
-            zps.append(zp)
-    fits = em_cluster_many(ctx, Xs, sims, zps, want_theta=False, reseed=reseed)
-    tm["mixture"] = time.perf_counter() - t1
-    # ---- stage 6: cluster consensus ----------------------------------------------------------
-    t1 = time.perf_counter()
-    cons_groups, cons_owner = [], []
-    plan = {}
-    for k, fit in zip(em_idx, fits):
-        ids = id_lists[k]
-        labels = fit["labels"]
-        som, germ = [], []
-        for lab in np.unique(labels):
-            members = np.where(labels == lab)[0]
-            kinds = np.unique([read_tag(x) for x in ids[members]])
-            if kinds.shape[0] == 1 and kinds[0] == Tlabel and members.shape[0] >= readcutoff:
-                som.append(members)
-            elif members.shape[0] >= readcutoff:
-                germ.append(members)
-        plan[k] = (som, germ)
-        if len(som) > 0:
-            for kind, lst in (("som", som), ("germ", germ)):
-                for c, members in enumerate(lst):
-                    src = [row_src[k][m] for m in members]
-                    nonzero = any(reads.off[s + 1] - reads.off[s] > 0 for s in src)
-                    cons_groups.append(src if nonzero else [])
-                    cons_owner.append((k, kind, c, nonzero))
-    cons, _, st_cons = poa_groups(ctx, reads, cons_groups, want_msa=False, strict=False)
-    bad_cons = {cons_owner[k][0] for k in np.flatnonzero(st_cons["status"])}
-    tm["poa_consensus"] = time.perf_counter() - t1
-    # ---- stage 7: records ----------------------------------------------------------------------
-    t1 = time.perf_counter()
-    seq_out: Dict[tuple, str] = {}
-    for (k, kind, c, nonzero), s in zip(cons_owner, cons):
-        seq_out[(k, kind, c)] = s if nonzero else "-"
-    for k, fit in zip(em_idx, fits):
-        i = live[k]
-        som, germ = plan[k]
-        ids = id_lists[k]
-        if keep_aux:
-            aux[i] = dict(K=fit["K"], labels=fit["labels"], gamma=fit["gamma"], pi=fit["pi"], bics=fit["bics"],
-                          n_redraws=fit["n_redraws"], nf=Xs[em_idx.index(k)].shape[1])
-        if k in bad_cons:
-            records[i][9] = flags[i] + "|GraphLimit"
-        elif len(som) > 0 and len(germ) > 0:                                  # DecisionMaker.py:178
-            rec = records[i]
-            records[i] = [rec[0], rec[1], rec[2],
-                          ";".join(seq_out[(k, "som", c)] for c in range(len(som))),
-                          ";".join(",".join(list(ids[m])) for m in som),
-                          len(som),
-                          ";".join(seq_out[(k, "germ", c)] for c in range(len(germ))),
-                          ";".join(",".join(list(ids[m])) for m in germ),
-                          len(germ),
-                          flags[i] + "|EMOutput"]
-    tm["records"] = time.perf_counter() - t1
-    # ---- optional: read-by-read edit distances ----------------------------------------------------
+    msa_jobs = [PoaJob(ctx, reads, [list(range(int(base[i]), int(base[i + 1]))) for i in part], want_msa=True)
+                for part in parts]
+    # ---- optional: read-by-read edit distances, behind the MSA kernels on a side thread -----------
     dists = None
     st_ed = dict(cells=0.0, ms=0.0, bytes=0.0, pairs=0.0)
+    ed_thread, ed_box = None, {}
     if edit_distance:
+        def _ed():
+            t_ed = time.perf_counter()
+            try:
+                ed_groups = [list(range(int(base[i]) + 1, int(base[i + 1]))) for i in live]
+                ed_box["mats"], ed_box["st"] = edit_distance_matrices(ctx, reads, ed_groups)
+            except BaseException as exc:   # re-raised on the main thread
+                ed_box["err"] = exc
+            ed_box["t"] = time.perf_counter() - t_ed
+        ed_thread = threading.Thread(target=_ed, daemon=True)
+        ed_thread.start()
+    tm["poa_msa"] += time.perf_counter() - t1
+    n_failed = 0
+    n_em = 0
+    n_redraw = 0
+    pending_cons = []
+    for part, job in zip(parts, msa_jobs):
         t1 = time.perf_counter()
-        ed_groups = [list(range(int(base[i]) + 1, int(base[i + 1]))) for i in live]
-        mats, st_ed = edit_distance_matrices(ctx, reads, ed_groups)
+        _, msas, st_msa = job.result(as_array=True, strict=False)
+        add_stats(st_msa)
+        tm["poa_msa"] += time.perf_counter() - t1
+        # ---- stage 3: encode, margins, features ---------------------------------------------------
+        t1 = time.perf_counter()
+        if st_msa["status"].any():
+            # a window the device cannot align (graph beyond the largest memory tier, more than 31
+            # in-edges at one node, ...) fails alone: flagged record, the batch goes on
+            for k in np.flatnonzero(st_msa["status"]):
+                records[part[k]][9] = flags[part[k]] + "|GraphLimit%d" % int(st_msa["status"][k])
+                n_failed += 1
+            ok = [k for k in range(len(part)) if st_msa["status"][k] == 0]
+            part = [part[k] for k in ok]
+            msas = [msas[k] for k in ok]
+        encs, drops, cutoffs, id_lists, row_src = [], [], [], [], []
+        for i, msa in zip(part, msas):
+            seqs, ids, f5, f3, _ = windows[i]
+            ids = np.asarray(ids)
+            lens = np.array([len(s) for s in seqs[1:]])
+            enc = encode_msa(msa)
+            nonempty = np.flatnonzero(lens != 0)
+            if nonempty.size != lens.size:
+                # DataScanner.py:198-209: gap rows are appended once per NON-empty read and the
+                # id list becomes the non-empty ids twice (the reference's own quirk)
+                kept = list(ids[nonempty])
+                enc = np.concatenate([enc, np.full((len(kept), enc.shape[1]), 4, enc.dtype)], axis=0)
+                ids = np.array(kept + kept)
+                src = [int(base[i]) + 1 + int(r) for r in nonempty] + [empty_idx] * len(kept)
+            else:
+                src = [int(base[i]) + 1 + r for r in range(len(lens))]
+            drop = np.zeros(enc.shape[1], np.uint8)
+            drop[margin_columns(msa[0], f5, f3)] = 1
+            encs.append(enc)
+            drops.append(drop)
+            cutoffs.append(float(max([hcutoff, enc.shape[0] * scutoff])))
+            id_lists.append(ids)
+            row_src.append(src)
+        feats = msa_features(ctx, [e[1:] for e in encs], drops, cutoffs)
+        tm["features"] += time.perf_counter() - t1
+        # ---- stage 4/5: mixture model ----------------------------------------------------------
+        t1 = time.perf_counter()
+        em_idx, Xs, sims, zps = [], [], [], []
+        for k, (enc, (keep, nf, zp, ident)) in enumerate(zip(encs, feats)):
+            n = enc.shape[0] - 1
+            if n != 0 and nf >= 10:                                            # DecisionMaker.py:137
+                X = np.ascontiguousarray(enc[1:][:, keep])
+                sim = ident.astype(np.float64) / nf
+                np.fill_diagonal(sim, 1.0)
+                em_idx.append(k)
+                Xs.append(X)
+                sims.append(sim)
+                zps.append(zp)
+        fits = em_cluster_many(ctx, Xs, sims, zps, want_theta=False, reseed=reseed)
+        n_em += len(em_idx)
+        n_redraw += sum(1 for f in fits if f["n_redraws"] > 0)
+        tm["mixture"] += time.perf_counter() - t1
+        # ---- stage 6: cluster consensus (submitted; collected after the next sub-batch) ------------
+        t1 = time.perf_counter()
+        cons_groups, cons_owner = [], []
+        plan = {}
+        for k, fit in zip(em_idx, fits):
+            ids = id_lists[k]
+            labels = fit["labels"]
+            som, germ = [], []
+            for lab in np.unique(labels):
+                members = np.where(labels == lab)[0]
+                kinds = np.unique([read_tag(x) for x in ids[members]])
+                if kinds.shape[0] == 1 and kinds[0] == Tlabel and members.shape[0] >= readcutoff:
+                    som.append(members)
+                elif members.shape[0] >= readcutoff:
+                    germ.append(members)
+            plan[k] = (som, germ)
+            if len(som) > 0:
+                for kind, lst in (("som", som), ("germ", germ)):
+                    for c, members in enumerate(lst):
+                        src = [row_src[k][m] for m in members]
+                        nonzero = any(reads.off[s + 1] - reads.off[s] > 0 for s in src)
+                        cons_groups.append(src if nonzero else [])
+                        cons_owner.append((k, kind, c, nonzero))
+        cjob = PoaJob(ctx, cons_reads, cons_groups, want_msa=False)
+        tm["poa_consensus"] += time.perf_counter() - t1
+        pending_cons.append((part, cjob, cons_owner, plan, em_idx, fits, id_lists, Xs))
+    # ---- stage 7: records ----------------------------------------------------------------------
+    for part, cjob, cons_owner, plan, em_idx, fits, id_lists, Xs in pending_cons:
+        t1 = time.perf_counter()
+        cons, _, st_cons = cjob.result(strict=False)
+        add_stats(st_cons)
+        bad_cons = {cons_owner[k][0] for k in np.flatnonzero(st_cons["status"])}
+        n_failed += len(bad_cons)
+        tm["poa_consensus"] += time.perf_counter() - t1
+        t1 = time.perf_counter()
+        seq_out: Dict[tuple, str] = {}
+        for (k, kind, c, nonzero), sq in zip(cons_owner, cons):
+            seq_out[(k, kind, c)] = sq if nonzero else "-"
+        for n_k, (k, fit) in enumerate(zip(em_idx, fits)):
+            i = part[k]
+            som, germ = plan[k]
+            ids = id_lists[k]
+            if keep_aux:
+                aux[i] = dict(K=fit["K"], labels=fit["labels"], gamma=fit["gamma"], pi=fit["pi"], bics=fit["bics"],
+                              n_redraws=fit["n_redraws"], nf=Xs[n_k].shape[1])
+            if k in bad_cons:
+                records[i][9] = flags[i] + "|GraphLimit"
+            elif len(som) > 0 and len(germ) > 0:                                  # DecisionMaker.py:178
+                rec = records[i]
+                records[i] = [rec[0], rec[1], rec[2],
+                              ";".join(seq_out[(k, "som", c)] for c in range(len(som))),
+                              ";".join(",".join(list(ids[m])) for m in som),
+                              len(som),
+                              ";".join(seq_out[(k, "germ", c)] for c in range(len(germ))),
+                              ";".join(",".join(list(ids[m])) for m in germ),
+                              len(germ),
+                              flags[i] + "|EMOutput"]
+        tm["records"] += time.perf_counter() - t1
+    if ed_thread is not None:
+        t1 = time.perf_counter()
+        ed_thread.join()
+        if "err" in ed_box:
+            raise ed_box["err"]
+        st_ed = ed_box["st"]
         dists = [None] * nw
-        for i, m in zip(live, mats):
-            dists[i] = m
-        tm["edit_distance"] = time.perf_counter() - t1
+        for i, mt in zip(live, ed_box["mats"]):
+            dists[i] = mt
+        tm["edit_distance"] = ed_box["t"]
+        tm["edit_distance_wait"] = time.perf_counter() - t1
+    if own_cons_reads:
+        cons_reads.close()
     tm["total"] = time.perf_counter() - t0
-    stats = {"poa_" + k: st_msa[k] + st_cons[k] for k in st_msa if k != "status"}
-    stats["poa_failed_windows"] = int(np.count_nonzero(st_msa["status"])) + len(bad_cons)
+    stats = {"poa_" + k: v for k, v in st_poa.items()}
+    stats["poa_failed_windows"] = n_failed
     stats.update({"ed_" + k: v for k, v in st_ed.items()})
     stats.update(ACCT)
     stats["windows"] = nw
     stats["windows_live"] = len(live)
-    stats["windows_em"] = len(em_idx)
-    stats["em_redraw_windows"] = sum(1 for f in fits if f["n_redraws"] > 0)
+    stats["windows_em"] = n_em
+    stats["em_redraw_windows"] = n_redraw
+    stats["sub_batches"] = nchunk
     return BatchOutput(records=records, timings=tm, stats=stats, edit_distances=dists,
                        aux=aux if keep_aux else None)

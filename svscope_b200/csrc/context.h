@@ -14,7 +14,7 @@ struct svs_ctx {
   int device = 0;
   std::string error;
   // options
-  int poa_threads = 128;   // 128 threads x 8 columns: four resident windows per SM
+  int poa_threads = 384;   // 384 threads x 8 columns: one resident window per SM, 12 warps on one alignment
   int prune = 1;       // exact score-bound pruning of DP cells (persistent kernel)
   int poa_cols = 8;    // read columns per thread (16 only with 256 threads)
   int ring_rows = 8;
@@ -31,6 +31,7 @@ struct svs_ctx {
   int sm_count = 0;
   int n_smid = 0;      // upper bound of %smid
   std::mutex mu;
+  std::mutex mu_ed;   // edit-distance calls (they may run on a side thread next to the other stages)
 };
 
 struct svs_reads {
@@ -63,5 +64,13 @@ inline int fail(svs_ctx* ctx, int code, const std::string& msg) {
 int ensure_arena(svs_ctx* ctx);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Copies on the calling thread's own stream, complete on return.  The per-thread stream does not
+// synchronise with the streams of the window kernel, and neither cudaFree nor a device-wide
+// synchronise is used by the auxiliary stages: both would wait for a running window kernel.
+inline cudaError_t svs_memcpy_pt(void* dst, const void* src, size_t n, cudaMemcpyKind kind) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, n, kind, cudaStreamPerThread);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(cudaStreamPerThread);
+}
 
 }  // namespace svs

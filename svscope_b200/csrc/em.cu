@@ -187,7 +187,7 @@ cudaError_t launch_k(const EmTask* d_tasks, const int32_t* d_ids, int n, size_t 
   if (n == 0) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(em_kernel<K, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  em_kernel<K, T><<<n, T, smem>>>(d_tasks, d_ids);
+  em_kernel<K, T><<<n, T, smem, cudaStreamPerThread>>>(d_tasks, d_ids);
   return cudaGetLastError();
 }
 
@@ -241,30 +241,30 @@ extern "C" int svs_em_batch(svs_ctx* ctx, int64_t n_tasks, const int8_t* X, cons
   int8_t* d_X = nullptr; int32_t *d_lab = nullptr, *d_status = nullptr, *d_ids = nullptr;
   double *d_g = nullptr, *d_th = nullptr, *d_pi = nullptr, *d_lik = nullptr; EmTask* d_tasks = nullptr;
   auto cleanup = [&]() {
-    cudaFree(d_X); cudaFree(d_lab); cudaFree(d_status); cudaFree(d_ids); cudaFree(d_g); cudaFree(d_th);
-    cudaFree(d_pi); cudaFree(d_lik); cudaFree(d_tasks);
+    ((d_X) ? cudaFreeAsync(d_X, cudaStreamPerThread) : cudaSuccess); ((d_lab) ? cudaFreeAsync(d_lab, cudaStreamPerThread) : cudaSuccess); ((d_status) ? cudaFreeAsync(d_status, cudaStreamPerThread) : cudaSuccess); ((d_ids) ? cudaFreeAsync(d_ids, cudaStreamPerThread) : cudaSuccess); ((d_g) ? cudaFreeAsync(d_g, cudaStreamPerThread) : cudaSuccess); ((d_th) ? cudaFreeAsync(d_th, cudaStreamPerThread) : cudaSuccess);
+    ((d_pi) ? cudaFreeAsync(d_pi, cudaStreamPerThread) : cudaSuccess); ((d_lik) ? cudaFreeAsync(d_lik, cudaStreamPerThread) : cudaSuccess); ((d_tasks) ? cudaFreeAsync(d_tasks, cudaStreamPerThread) : cudaSuccess);
   };
 #define SVS_CU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); \
     return fail(ctx, SVS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
-  SVS_CU(cudaMalloc(&d_X, x_total + 16));
-  SVS_CU(cudaMalloc(&d_lab, (lab_total + 4) * sizeof(int32_t)));
-  SVS_CU(cudaMalloc(&d_status, n_tasks * sizeof(int32_t)));
-  SVS_CU(cudaMalloc(&d_ids, n_tasks * sizeof(int32_t)));
-  SVS_CU(cudaMalloc(&d_g, (g_total + 2) * sizeof(double)));
-  SVS_CU(cudaMalloc(&d_th, (th_total + 2) * sizeof(double)));
-  SVS_CU(cudaMalloc(&d_pi, (pi_total + 2) * sizeof(double)));
-  SVS_CU(cudaMalloc(&d_lik, (lik_total + 2) * sizeof(double)));
-  SVS_CU(cudaMalloc(&d_tasks, n_tasks * sizeof(EmTask)));
-  SVS_CU(cudaMemcpy(d_X, X, x_total, cudaMemcpyHostToDevice));
-  if (lab_total) SVS_CU(cudaMemcpy(d_lab, init_labels, lab_total * sizeof(int32_t), cudaMemcpyHostToDevice));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_X), x_total + 16, cudaStreamPerThread));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_lab), (lab_total + 4) * sizeof(int32_t), cudaStreamPerThread));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_status), n_tasks * sizeof(int32_t), cudaStreamPerThread));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_ids), n_tasks * sizeof(int32_t), cudaStreamPerThread));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_g), (g_total + 2) * sizeof(double), cudaStreamPerThread));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_th), (th_total + 2) * sizeof(double), cudaStreamPerThread));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_pi), (pi_total + 2) * sizeof(double), cudaStreamPerThread));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_lik), (lik_total + 2) * sizeof(double), cudaStreamPerThread));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_tasks), n_tasks * sizeof(EmTask), cudaStreamPerThread));
+  SVS_CU(svs_memcpy_pt(d_X, X, x_total, cudaMemcpyHostToDevice));
+  if (lab_total) SVS_CU(svs_memcpy_pt(d_lab, init_labels, lab_total * sizeof(int32_t), cudaMemcpyHostToDevice));
   // start states given as theta/pi travel to the device; the rest is output only
   if ((want_theta || any_from_theta) && !theta_io) { cleanup(); return fail(ctx, SVS_ERR_ARG, "theta buffer required"); }
   for (int64_t t = 0; t < n_tasks && any_from_theta; ++t) {
     if (lab_off[t] >= 0) continue;
-    SVS_CU(cudaMemcpy(d_th + theta_off[t], theta_io + theta_off[t],
+    SVS_CU(svs_memcpy_pt(d_th + theta_off[t], theta_io + theta_off[t],
                       static_cast<size_t>(K[t]) * nf[t] * kA * sizeof(double), cudaMemcpyHostToDevice));
   }
-  SVS_CU(cudaMemcpy(d_pi, pi_io, pi_total * sizeof(double), cudaMemcpyHostToDevice));
+  SVS_CU(svs_memcpy_pt(d_pi, pi_io, pi_total * sizeof(double), cudaMemcpyHostToDevice));
   std::vector<EmTask> tasks(n_tasks);
   std::vector<std::vector<int32_t>> by_class(18);  // (K-1)*2 + big
   std::vector<size_t> smem_class(18, 0);
@@ -288,7 +288,7 @@ extern "C" int svs_em_batch(svs_ctx* ctx, int64_t n_tasks, const int8_t* X, cons
     by_class[cls].push_back(static_cast<int32_t>(t));
     smem_class[cls] = std::max(smem_class[cls], em_smem_bytes(N[t], K[t], T, ft));
   }
-  SVS_CU(cudaMemcpy(d_tasks, tasks.data(), n_tasks * sizeof(EmTask), cudaMemcpyHostToDevice));
+  SVS_CU(svs_memcpy_pt(d_tasks, tasks.data(), n_tasks * sizeof(EmTask), cudaMemcpyHostToDevice));
   std::vector<int32_t> ids;
   std::vector<size_t> cls_off(19, 0);
   for (int c = 0; c < 18; ++c) {
@@ -296,7 +296,7 @@ extern "C" int svs_em_batch(svs_ctx* ctx, int64_t n_tasks, const int8_t* X, cons
     ids.insert(ids.end(), by_class[c].begin(), by_class[c].end());
   }
   cls_off[18] = ids.size();
-  SVS_CU(cudaMemcpy(d_ids, ids.data(), ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  SVS_CU(svs_memcpy_pt(d_ids, ids.data(), ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   for (int c = 0; c < 18; ++c) {
     const int n = static_cast<int>(by_class[c].size());
     if (!n) continue;
@@ -305,12 +305,12 @@ extern "C" int svs_em_batch(svs_ctx* ctx, int64_t n_tasks, const int8_t* X, cons
     if (c & 1) SVS_CU(launch<1024>(Kc, d_tasks, d_ids + cls_off[c], n, smem_class[c]));
     else SVS_CU(launch<256>(Kc, d_tasks, d_ids + cls_off[c], n, smem_class[c]));
   }
-  SVS_CU(cudaDeviceSynchronize());
-  SVS_CU(cudaMemcpy(gamma, d_g, g_total * sizeof(double), cudaMemcpyDeviceToHost));
-  if (want_theta && th_total) SVS_CU(cudaMemcpy(theta_io, d_th, th_total * sizeof(double), cudaMemcpyDeviceToHost));
-  SVS_CU(cudaMemcpy(pi_io, d_pi, pi_total * sizeof(double), cudaMemcpyDeviceToHost));
-  SVS_CU(cudaMemcpy(loglik, d_lik, lik_total * sizeof(double), cudaMemcpyDeviceToHost));
-  SVS_CU(cudaMemcpy(status, d_status, n_tasks * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  SVS_CU(cudaStreamSynchronize(cudaStreamPerThread));
+  SVS_CU(svs_memcpy_pt(gamma, d_g, g_total * sizeof(double), cudaMemcpyDeviceToHost));
+  if (want_theta && th_total) SVS_CU(svs_memcpy_pt(theta_io, d_th, th_total * sizeof(double), cudaMemcpyDeviceToHost));
+  SVS_CU(svs_memcpy_pt(pi_io, d_pi, pi_total * sizeof(double), cudaMemcpyDeviceToHost));
+  SVS_CU(svs_memcpy_pt(loglik, d_lik, lik_total * sizeof(double), cudaMemcpyDeviceToHost));
+  SVS_CU(svs_memcpy_pt(status, d_status, n_tasks * sizeof(int32_t), cudaMemcpyDeviceToHost));
 #undef SVS_CU
   cleanup();
   return SVS_OK;

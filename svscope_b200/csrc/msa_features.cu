@@ -91,19 +91,19 @@ extern "C" int svs_msa_features(svs_ctx* ctx, int64_t n_windows, const int8_t* e
   int8_t* d_enc = nullptr; uint8_t *d_drop = nullptr, *d_keep = nullptr;
   int32_t *d_ident = nullptr, *d_cnt = nullptr; FeatTask* d_tasks = nullptr;
   auto cleanup = [&]() {
-    cudaFree(d_enc); cudaFree(d_drop); cudaFree(d_keep); cudaFree(d_ident); cudaFree(d_cnt); cudaFree(d_tasks);
+    ((d_enc) ? cudaFreeAsync(d_enc, cudaStreamPerThread) : cudaSuccess); ((d_drop) ? cudaFreeAsync(d_drop, cudaStreamPerThread) : cudaSuccess); ((d_keep) ? cudaFreeAsync(d_keep, cudaStreamPerThread) : cudaSuccess); ((d_ident) ? cudaFreeAsync(d_ident, cudaStreamPerThread) : cudaSuccess); ((d_cnt) ? cudaFreeAsync(d_cnt, cudaStreamPerThread) : cudaSuccess); ((d_tasks) ? cudaFreeAsync(d_tasks, cudaStreamPerThread) : cudaSuccess);
   };
 #define SVS_CU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); \
     return fail(ctx, SVS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
-  SVS_CU(cudaMalloc(&d_enc, enc_bytes + 16));
-  SVS_CU(cudaMalloc(&d_drop, col_total + 16));
-  SVS_CU(cudaMalloc(&d_keep, col_total + 16));
-  SVS_CU(cudaMalloc(&d_ident, (ident_total + 4) * sizeof(int32_t)));
-  SVS_CU(cudaMalloc(&d_cnt, 2 * n_windows * sizeof(int32_t)));
-  SVS_CU(cudaMalloc(&d_tasks, n_windows * sizeof(FeatTask)));
-  SVS_CU(cudaMemcpy(d_enc, enc, enc_bytes, cudaMemcpyHostToDevice));
-  SVS_CU(cudaMemcpy(d_drop, drop, col_total, cudaMemcpyHostToDevice));
-  SVS_CU(cudaMemset(d_cnt, 0, 2 * n_windows * sizeof(int32_t)));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_enc), enc_bytes + 16, cudaStreamPerThread));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_drop), col_total + 16, cudaStreamPerThread));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_keep), col_total + 16, cudaStreamPerThread));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_ident), (ident_total + 4) * sizeof(int32_t), cudaStreamPerThread));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_cnt), 2 * n_windows * sizeof(int32_t), cudaStreamPerThread));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_tasks), n_windows * sizeof(FeatTask), cudaStreamPerThread));
+  SVS_CU(svs_memcpy_pt(d_enc, enc, enc_bytes, cudaMemcpyHostToDevice));
+  SVS_CU(svs_memcpy_pt(d_drop, drop, col_total, cudaMemcpyHostToDevice));
+  SVS_CU(cudaMemsetAsync(d_cnt, 0, 2 * n_windows * sizeof(int32_t), cudaStreamPerThread));
   std::vector<FeatTask> tasks(n_windows);
   int max_rows = 0, max_cols = 0;
   for (int64_t w = 0; w < n_windows; ++w) {
@@ -119,22 +119,22 @@ extern "C" int svs_msa_features(svs_ctx* ctx, int64_t n_windows, const int8_t* e
     max_rows = std::max(max_rows, t.n_rows);
     max_cols = std::max(max_cols, t.n_cols);
   }
-  SVS_CU(cudaMemcpy(d_tasks, tasks.data(), n_windows * sizeof(FeatTask), cudaMemcpyHostToDevice));
+  SVS_CU(svs_memcpy_pt(d_tasks, tasks.data(), n_windows * sizeof(FeatTask), cudaMemcpyHostToDevice));
   if (max_cols > 0 && max_rows > 0) {
     const dim3 g1((max_cols + 255) / 256, static_cast<unsigned>(n_windows));
-    column_stats_kernel<<<g1, 256>>>(d_tasks);
+    column_stats_kernel<<<g1, 256, 0, cudaStreamPerThread>>>(d_tasks);
     SVS_CU(cudaGetLastError());
     const dim3 g2(max_rows, static_cast<unsigned>(n_windows));
-    identity_kernel<<<g2, 256>>>(d_tasks);
+    identity_kernel<<<g2, 256, 0, cudaStreamPerThread>>>(d_tasks);
     SVS_CU(cudaGetLastError());
   } else {
-    SVS_CU(cudaMemset(d_keep, 0, col_total + 16));
+    SVS_CU(cudaMemsetAsync(d_keep, 0, col_total + 16, cudaStreamPerThread));
   }
-  SVS_CU(cudaDeviceSynchronize());
-  if (col_total) SVS_CU(cudaMemcpy(keep, d_keep, col_total, cudaMemcpyDeviceToHost));
-  if (ident_total) SVS_CU(cudaMemcpy(ident, d_ident, ident_total * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  SVS_CU(cudaStreamSynchronize(cudaStreamPerThread));
+  if (col_total) SVS_CU(svs_memcpy_pt(keep, d_keep, col_total, cudaMemcpyDeviceToHost));
+  if (ident_total) SVS_CU(svs_memcpy_pt(ident, d_ident, ident_total * sizeof(int32_t), cudaMemcpyDeviceToHost));
   std::vector<int32_t> cnt(2 * n_windows);
-  SVS_CU(cudaMemcpy(cnt.data(), d_cnt, cnt.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  SVS_CU(svs_memcpy_pt(cnt.data(), d_cnt, cnt.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
   for (int64_t w = 0; w < n_windows; ++w) {
     nf[w] = cnt[2 * w];
     zero_params[w] = cnt[2 * w + 1];

@@ -152,16 +152,16 @@ cudaError_t launch_class(int c, const PairTask* d_tasks, const int32_t* d_ids, i
   const int block = 128;
   const unsigned blocks = static_cast<unsigned>((static_cast<int64_t>(n) * 32 + block - 1) / block);
   switch (kClasses[c]) {
-    case 1: myers_kernel<1><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
-    case 2: myers_kernel<2><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
-    case 4: myers_kernel<4><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
-    case 6: myers_kernel<6><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
-    case 8: myers_kernel<8><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
-    case 10: myers_kernel<10><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
-    case 12: myers_kernel<12><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
-    case 16: myers_kernel<16><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
-    case 24: myers_kernel<24><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
-    default: myers_kernel<32><<<blocks, block>>>(d_tasks, d_ids, d_dist, n); break;
+    case 1: myers_kernel<1><<<blocks, block, 0, cudaStreamPerThread>>>(d_tasks, d_ids, d_dist, n); break;
+    case 2: myers_kernel<2><<<blocks, block, 0, cudaStreamPerThread>>>(d_tasks, d_ids, d_dist, n); break;
+    case 4: myers_kernel<4><<<blocks, block, 0, cudaStreamPerThread>>>(d_tasks, d_ids, d_dist, n); break;
+    case 6: myers_kernel<6><<<blocks, block, 0, cudaStreamPerThread>>>(d_tasks, d_ids, d_dist, n); break;
+    case 8: myers_kernel<8><<<blocks, block, 0, cudaStreamPerThread>>>(d_tasks, d_ids, d_dist, n); break;
+    case 10: myers_kernel<10><<<blocks, block, 0, cudaStreamPerThread>>>(d_tasks, d_ids, d_dist, n); break;
+    case 12: myers_kernel<12><<<blocks, block, 0, cudaStreamPerThread>>>(d_tasks, d_ids, d_dist, n); break;
+    case 16: myers_kernel<16><<<blocks, block, 0, cudaStreamPerThread>>>(d_tasks, d_ids, d_dist, n); break;
+    case 24: myers_kernel<24><<<blocks, block, 0, cudaStreamPerThread>>>(d_tasks, d_ids, d_dist, n); break;
+    default: myers_kernel<32><<<blocks, block, 0, cudaStreamPerThread>>>(d_tasks, d_ids, d_dist, n); break;
   }
   return cudaGetLastError();
 }
@@ -192,14 +192,14 @@ int run_pairs(svs_ctx* ctx, const svs_reads* reads, const std::vector<int64_t>& 
   PairTask* d_tasks = nullptr; int32_t* d_dist = nullptr; int8_t* d_bnd = nullptr; int32_t* d_ids = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   auto cleanup = [&]() {
-    cudaFree(d_tasks); cudaFree(d_dist); cudaFree(d_bnd); cudaFree(d_ids);
+    ((d_tasks) ? cudaFreeAsync(d_tasks, cudaStreamPerThread) : cudaSuccess); ((d_dist) ? cudaFreeAsync(d_dist, cudaStreamPerThread) : cudaSuccess); ((d_bnd) ? cudaFreeAsync(d_bnd, cudaStreamPerThread) : cudaSuccess); ((d_ids) ? cudaFreeAsync(d_ids, cudaStreamPerThread) : cudaSuccess);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
   };
 #define SVS_CU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); \
     return fail(ctx, SVS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
   if (bnd_total) {
-    SVS_CU(cudaMalloc(&d_bnd, bnd_total));
+    SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_bnd), bnd_total, cudaStreamPerThread));
     size_t off = 0;
     for (int64_t k = 0; k < n; ++k) {
       if (tasks[k].la > strip_cap) {
@@ -208,9 +208,9 @@ int run_pairs(svs_ctx* ctx, const svs_reads* reads, const std::vector<int64_t>& 
       }
     }
   }
-  SVS_CU(cudaMalloc(&d_tasks, n * sizeof(PairTask)));
-  SVS_CU(cudaMalloc(&d_dist, n * sizeof(int32_t)));
-  SVS_CU(cudaMemcpy(d_tasks, tasks.data(), n * sizeof(PairTask), cudaMemcpyHostToDevice));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_tasks), n * sizeof(PairTask), cudaStreamPerThread));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_dist), n * sizeof(int32_t), cudaStreamPerThread));
+  SVS_CU(svs_memcpy_pt(d_tasks, tasks.data(), n * sizeof(PairTask), cudaMemcpyHostToDevice));
   SVS_CU(cudaEventCreate(&e0));
   SVS_CU(cudaEventCreate(&e1));
   // pairs grouped by words-per-lane class; inside a class longest text first
@@ -225,9 +225,9 @@ int run_pairs(svs_ctx* ctx, const svs_reads* reads, const std::vector<int64_t>& 
     ids.insert(ids.end(), v.begin(), v.end());
   }
   coff[kNumClasses] = ids.size();
-  SVS_CU(cudaMalloc(&d_ids, n * sizeof(int32_t)));
-  SVS_CU(cudaMemcpy(d_ids, ids.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
-  SVS_CU(cudaEventRecord(e0));
+  SVS_CU(cudaMallocAsync(reinterpret_cast<void**>(&d_ids), n * sizeof(int32_t), cudaStreamPerThread));
+  SVS_CU(svs_memcpy_pt(d_ids, ids.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  SVS_CU(cudaEventRecord(e0, cudaStreamPerThread));
   int launches = 0;
   for (int c = kNumClasses - 1; c >= 0; --c) {
     const int nc = static_cast<int>(by_class[c].size());
@@ -235,11 +235,11 @@ int run_pairs(svs_ctx* ctx, const svs_reads* reads, const std::vector<int64_t>& 
     SVS_CU(launch_class(c, d_tasks, d_ids + coff[c], d_dist, nc));
     ++launches;
   }
-  SVS_CU(cudaEventRecord(e1));
-  SVS_CU(cudaDeviceSynchronize());
+  SVS_CU(cudaEventRecord(e1, cudaStreamPerThread));
+  SVS_CU(cudaStreamSynchronize(cudaStreamPerThread));
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
-  SVS_CU(cudaMemcpy(out, d_dist, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  SVS_CU(svs_memcpy_pt(out, d_dist, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
 #undef SVS_CU
   cleanup();
   if (stats) {
@@ -265,7 +265,7 @@ extern "C" {
 int svs_edit_distance_pairs(svs_ctx* ctx, const svs_reads* reads, const int64_t* a, const int64_t* b,
                             int64_t n_pairs, int32_t* dist, double* stats, int n_stats) {
   if (!ctx || !reads || n_pairs < 0) return fail(ctx, SVS_ERR_ARG, "null argument");
-  std::lock_guard<std::mutex> lock(ctx->mu);
+  std::lock_guard<std::mutex> lock(ctx->mu_ed);
   if (!only_acgt(reads)) return fail(ctx, SVS_ERR_UNSUPPORTED, "edit distance kernel expects upper-case A,C,G,T");
   std::vector<int64_t> va(a, a + n_pairs), vb(b, b + n_pairs);
   return run_pairs(ctx, reads, va, vb, dist, stats, n_stats);
@@ -274,7 +274,7 @@ int svs_edit_distance_pairs(svs_ctx* ctx, const svs_reads* reads, const int64_t*
 int svs_edit_distance_matrix(svs_ctx* ctx, const svs_reads* reads, const int64_t* members, const int64_t* group_off,
                              int64_t n_groups, int32_t* dist, const int64_t* dist_off, double* stats, int n_stats) {
   if (!ctx || !reads || n_groups < 0) return fail(ctx, SVS_ERR_ARG, "null argument");
-  std::lock_guard<std::mutex> lock(ctx->mu);
+  std::lock_guard<std::mutex> lock(ctx->mu_ed);
   if (!only_acgt(reads)) return fail(ctx, SVS_ERR_UNSUPPORTED, "edit distance kernel expects upper-case A,C,G,T");
   std::vector<int64_t> va, vb;
   std::vector<int64_t> where;  // output index of dist[i][j]

@@ -107,12 +107,14 @@ double group_cost(const WinCaps& c) {
   return n * lbar * lbar * (1.0 + 0.02 * n);
 }
 
+// (stream-ordered frees: cudaFree would wait for every kernel on the device, i.e. for the window
+// kernels of the other sub-batches that are still running)
 void free_round(svs_poa_result* r) {
-  if (r->d_members) cudaFree(r->d_members);
-  if (r->d_desc) cudaFree(r->d_desc);
-  if (r->d_order) cudaFree(r->d_order);
-  if (r->d_res) cudaFree(r->d_res);
-  if (r->d_counter) cudaFree(r->d_counter);
+  if (r->d_members) cudaFreeAsync(r->d_members, r->stream);
+  if (r->d_desc) cudaFreeAsync(r->d_desc, r->stream);
+  if (r->d_order) cudaFreeAsync(r->d_order, r->stream);
+  if (r->d_res) cudaFreeAsync(r->d_res, r->stream);
+  if (r->d_counter) cudaFreeAsync(r->d_counter, r->stream);
   r->d_members = nullptr; r->d_desc = nullptr; r->d_order = nullptr; r->d_res = nullptr; r->d_counter = nullptr;
 }
 
@@ -140,13 +142,13 @@ int launch_round(svs_poa_result* r, const std::vector<int>& groups, int tier_idx
     out_need += static_cast<uint64_t>((r->want_msa ? c.nseq * cols : 0) + c.lmax + cols + 64);
   }
   free_round(r);
-  SVS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&r->d_desc), sizeof(WinDesc) * n));
-  SVS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&r->d_order), sizeof(int32_t) * n));
-  SVS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&r->d_res), sizeof(WinResult) * n));
-  SVS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&r->d_counter), 64));
-  SVS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&r->d_members), sizeof(int64_t) * std::max<size_t>(1, r->members.size())));
+  SVS_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&r->d_desc), sizeof(WinDesc) * n, r->stream));
+  SVS_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&r->d_order), sizeof(int32_t) * n, r->stream));
+  SVS_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&r->d_res), sizeof(WinResult) * n, r->stream));
+  SVS_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&r->d_counter), 64, r->stream));
+  SVS_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&r->d_members), sizeof(int64_t) * std::max<size_t>(1, r->members.size()), r->stream));
   uint8_t* d_out = nullptr;
-  SVS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&d_out), out_need));
+  SVS_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&d_out), out_need, r->stream));
   r->out_bufs.push_back(d_out);
   cudaStream_t st = r->stream;
   SVS_CUDA(ctx, cudaMemcpyAsync(r->d_desc, desc.data(), sizeof(WinDesc) * n, cudaMemcpyHostToDevice, st));
@@ -283,9 +285,9 @@ int submit(svs_ctx* ctx, const svs_reads* reads, const int64_t* members, const i
   SVS_CUDA(ctx, cudaEventCreate(&r->ev1));
   if (debug_pairs) {
     r->pairs_cap = pairs_total;
-    SVS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&r->d_pairs), sizeof(int32_t) * 2 * std::max<int64_t>(1, pairs_total)));
-    SVS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&r->d_pair_cnt), sizeof(int64_t) * std::max<size_t>(1, r->members.size())));
-    SVS_CUDA(ctx, cudaMemset(r->d_pair_cnt, 0, sizeof(int64_t) * std::max<size_t>(1, r->members.size())));
+    SVS_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&r->d_pairs), sizeof(int32_t) * 2 * std::max<int64_t>(1, pairs_total), r->stream));
+    SVS_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&r->d_pair_cnt), sizeof(int64_t) * std::max<size_t>(1, r->members.size()), r->stream));
+    SVS_CUDA(ctx, cudaMemsetAsync(r->d_pair_cnt, 0, sizeof(int64_t) * std::max<size_t>(1, r->members.size()), r->stream));
   }
   // windows whose fixed part does not even fit a tier-0 slot start from the first tier that holds them
   std::vector<int> t0;
@@ -457,9 +459,9 @@ void svs_poa_result_free(svs_poa_result* res) {
   cudaSetDevice(res->ctx->device);
   if (res->pending && res->ev1) cudaEventSynchronize(res->ev1);
   free_round(res);
-  for (uint8_t* b : res->out_bufs) cudaFree(b);
-  if (res->d_pairs) cudaFree(res->d_pairs);
-  if (res->d_pair_cnt) cudaFree(res->d_pair_cnt);
+  for (uint8_t* b : res->out_bufs) cudaFreeAsync(b, res->stream);
+  if (res->d_pairs) cudaFreeAsync(res->d_pairs, res->stream);
+  if (res->d_pair_cnt) cudaFreeAsync(res->d_pair_cnt, res->stream);
   if (res->ev0) cudaEventDestroy(res->ev0);
   if (res->ev1) cudaEventDestroy(res->ev1);
   if (res->stream) cudaStreamDestroy(res->stream);

@@ -41,14 +41,14 @@ def _random_group(rng, it, lmax=400):
     return seqs
 
 
-@pytest.mark.parametrize("threads,ring,cols,dp", [(128, 8, 8, 2), (512, 8, 8, 2), (256, 10, 8, 2), (128, 1, 8, 2),
+@pytest.mark.parametrize("threads,ring,cols,dp", [(384, 8, 8, 2), (128, 8, 8, 2), (512, 8, 8, 2), (384, 2, 8, 2), (256, 10, 8, 2), (128, 1, 8, 2),
                                                   (512, 3, 8, 2), (128, 24, 8, 2), (128, 2, 8, 2), (256, 5, 8, 2),
                                                   (256, 1, 8, 2), (512, 1, 8, 2)])
 def test_alignment_pairs_bit_exact(ctx, oracle, threads, ring, cols, dp):
     """Every alignment (node id, read position) list equals the oracle's, for several CTA
     sizes and ring depths (ring 1 forces almost every non-adjacent predecessor through the
     exported rows in global memory).  All shapes run the window kernel (graph resident on the
-    device); the default is 128 threads x 8 columns with a ring of 8 rows (four resident windows per SM)."""
+    device); the default is 384 threads x 8 columns with a ring of 8 rows (one resident window per SM)."""
     from svscope_b200.poa_api import align_pairs
     ctx.set_option("poa_threads", threads)
     ctx.set_option("ring_rows", ring)
@@ -65,7 +65,7 @@ def test_alignment_pairs_bit_exact(ctx, oracle, threads, ring, cols, dp):
                 assert a.shape == b.shape and np.array_equal(a, b)
             o.close()
     finally:
-        ctx.set_option("poa_threads", 128)
+        ctx.set_option("poa_threads", 384)
         ctx.set_option("ring_rows", 8)
         ctx.set_option("poa_cols", 8)
         ctx.set_option("dp_kernel", 2)

@@ -448,8 +448,21 @@ def _device_stand_ins(oracle, monkeypatch):
             out.append((keep, int(keep.sum()), oracle.zero_param_num(X) if X.size else 0, ident))
         return out
 
+    class FakeJob:
+        """stand-in for poa_api.PoaJob (svs_poa_submit / svs_poa_wait)"""
+        def __init__(self, ctx, reads, groups, algorithm=1, want_msa=True, scores=None):
+            self.args = (ctx, reads, groups, algorithm, want_msa, scores)
+
+        def result(self, as_array=False, strict=True):
+            ctx, reads, groups, algorithm, want_msa, scores = self.args
+            return fake_poa_groups(ctx, reads, groups, algorithm, want_msa, scores, as_array, strict)
+
+        def close(self):
+            pass
+
     monkeypatch.setattr(batch, "upload_windows", fake_upload)
     monkeypatch.setattr(batch, "poa_groups", fake_poa_groups)
+    monkeypatch.setattr(poa_api, "PoaJob", FakeJob)
     monkeypatch.setattr(batch, "msa_features", fake_msa_features)
     monkeypatch.setattr(batch, "em_batch", _fake_em_batch(oracle))
 
