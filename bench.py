@@ -13,8 +13,12 @@ N>1 (torchrun, one rank per GPU): every rank gets its own batch of the same dist
 `value`   device-resident: the reads are uploaded to HBM before the timed region.
 `e2e`     the same step through the public batch call with host buffers (read upload and all
           result copies inside the timed region).
+Batch size of a step: the configs[1] batch (1000 windows) unless K steps of it would not fit
+`--budget-s` seconds (the driver allows 870 s per run); then every step takes the first n
+windows of the batch, n chosen from one untimed full-size step, and the JSON line says so
+(`config.windows_per_step`).  Warm-up steps run on a 64-window slice (context, arena, kernels).
 `--impl reference`  times the CPU path (oracle port of the reference: pyspoa is not
-          installable offline) on a bounded sample with all host cores.
+          installable offline) on a bounded sample with all host cores, once.
 """
 from __future__ import annotations
 
@@ -33,10 +37,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before any CUDA context (see svscope_b200/__init__.py)
 
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 15.59e9   # profiles/r01_poa_persistent_kernel_final_ncu_full.txt (one launch, 296 alignments)
 METRIC = "localGraph windows/sec"
 UNIT = "windows/s"
 WORKLOAD = "configs[1]: synthetic INS/DEL windows, 30 tumor + 30 normal reads, 5-15 kb, 5% error"
+CONFIGS1_BATCH = 1000
+# dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the window kernel
+# (profiles/r02_poa_window_kernel_128x8_2cta_ncu_full.txt: 2 windows x 61 reads of 3 kb, 120 alignments)
+NCU_TRAFFIC = {"bytes": 1.478912e6 + 1.219072e6, "alignments": 120.0}
 
 
 # ------------------------------------------------------------------------------------------
@@ -80,12 +87,13 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                pw.append(float(r[3]))
                 for nm, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
@@ -93,7 +101,7 @@ class ClockSampler:
                 pass
         busy = [v for v in sm if v > 0]
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_median": statistics.median(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def dist_setup(n_gpus):
@@ -121,24 +129,26 @@ def barrier_sync():
         torch.cuda.synchronize()
 
 
-def max_over_ranks(x: float) -> float:
+def _reduce(x: float, op_name: str) -> float:
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         return x
     t = torch.tensor([x], dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=getattr(dist.ReduceOp, op_name))
     return float(t.item())
 
 
-def sum_over_ranks(x: float) -> float:
-    import torch
-    import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()):
-        return x
-    t = torch.tensor([x], dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
+def max_over_ranks(x):
+    return _reduce(x, "MAX")
+
+
+def min_over_ranks(x):
+    return _reduce(x, "MIN")
+
+
+def sum_over_ranks(x):
+    return _reduce(x, "SUM")
 
 
 def make_batch(n_windows, rank):
@@ -147,69 +157,107 @@ def make_batch(n_windows, rank):
 
 
 # ------------------------------------------------------------------------------------------
-# CPU path (oracle port of the reference) on a bounded sample
+# CPU path (oracle port of the reference) on a bounded, cost-stratified sample
 # ------------------------------------------------------------------------------------------
-def _cpu_one(w):
+def model_cells(window, new_node_rate=0.035):
+    """Nominal DP cells of the window MSA, sum over reads of (|V| + 1)(L + 1), with the graph
+    growing by `new_node_rate` nodes per aligned base (substitutions + insertions of the 5 %
+    error model).  Used to place windows in cost strata and, in the reference arm, to turn
+    the measured CPU cell rate into windows/s; the ours arm prints the residual of this model
+    against the cells the device counted."""
+    seqs = window[0]
+    V = float(len(seqs[0]))
+    cells = 0.0
+    for s in seqs[1:]:
+        cells += (V + 1.0) * (len(s) + 1.0)
+        V += new_node_rate * len(s)
+    return cells
+
+
+def _cpu_worker(args):
+    """One window on one core until the deadline: window MSA read by read (cells counted by the
+    oracle engine), then a slice of the read-by-read Levenshtein matrix."""
+    seqs, budget_s, ed_budget_s = args
     from oracle import oracle as O
     t0 = time.perf_counter()
-    rec = O.decision(w[4], w[0], w[1], w[2], w[3])
-    O.levenshtein_matrix(w[0][1:], bitparallel=True)
-    return rec[-1], time.perf_counter() - t0
-
-
-def cpu_sample(windows, budget_s=25.0, cores=None):
-    """Cheapest windows first until the cost model predicts ~budget_s per core."""
-    from svscope_b200 import synth
-    cores = cores or os.cpu_count() or 1
-    costs = np.array([synth.window_cost(w) for w in windows])
-    order = np.argsort(costs)
-    rate = 1.5e8  # cost units per core-second (measured: ~0.1-0.2 GCUPS scalar five-matrix DP)
-    picked, load = [], 0.0
-    for i in order:
-        if picked and (load + costs[i]) / rate > budget_s * cores:
+    sess = O.PoaSession(1)
+    cells, n_done = 0.0, 0
+    for s in seqs:
+        sess.add(s)
+        cells += float(O.lib().spo_last_cells(sess._h))
+        n_done += 1
+        if time.perf_counter() - t0 > budget_s:
             break
-        picked.append(int(i))
-        load += costs[i]
-        if len(picked) >= 4 * cores:
-            break
-    return picked, costs
+    t_poa = time.perf_counter() - t0
+    sess.close()
+    t1 = time.perf_counter()
+    ed_cells, k = 0.0, 0
+    reads = seqs[1:]
+    while time.perf_counter() - t1 < ed_budget_s and k + 1 < len(reads):
+        O.levenshtein(reads[k], reads[k + 1], bitparallel=True)
+        ed_cells += float(len(reads[k])) * float(len(reads[k + 1]))
+        k += 1
+    t_ed = time.perf_counter() - t1
+    return dict(cells=cells, t_poa=t_poa, alignments=n_done, complete=n_done == len(seqs), ed_cells=ed_cells, t_ed=t_ed)
 
 
-def run_cpu(windows, budget_s, cores=None):
+def cpu_rates(windows, budget_s=20.0, cores=None):
+    """Scalar-port rates on `cores` windows spread evenly over the cost-sorted batch, one process each."""
     import multiprocessing as mp
-    cores = cores or os.cpu_count() or 1
-    picked, costs = cpu_sample(windows, budget_s, cores)
-    sample = [windows[i] for i in picked]
+    cores = min(cores or os.cpu_count() or 1, len(windows))
+    costs = np.array([model_cells(w) for w in windows])
+    order = np.argsort(costs)
+    picks = [int(order[int((k + 0.5) * len(order) / cores)]) for k in range(cores)]
+    jobs = [(list(windows[i][0]), budget_s, max(2.0, 0.15 * budget_s)) for i in picks]
     t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(min(cores, len(sample))) as pool:
-        res = pool.map(_cpu_one, sample, chunksize=1)
-    dt = time.perf_counter() - t0
-    raw = len(sample) / dt
-    scale = float(costs[picked].mean() / costs.mean())   # sample is cheaper than the batch average
-    return dict(value=raw * scale, raw_windows_per_s=raw, seconds=dt, n=len(sample), cores=min(cores, len(sample)),
-                cost_scale=scale,
-                sample=f"{len(sample)} cheapest of {len(windows)} windows (mean cost {scale:.2f}x of the batch mean; "
-                       f"value = sample windows/s x that ratio), one process per window on {min(cores, len(sample))} cores, "
-                       f"{dt:.1f} s wall")
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    poa_rate = sum(r["cells"] for r in res) / max(1e-9, sum(r["t_poa"] for r in res))      # cells / core-second
+    ed_rate = sum(r["ed_cells"] for r in res) / max(1e-9, sum(r["t_ed"] for r in res))
+    return dict(cores=cores, poa_cells_per_core_s=poa_rate, ed_cells_per_core_s=ed_rate, wall_s=wall,
+                alignments=sum(r["alignments"] for r in res), windows_completed=sum(r["complete"] for r in res),
+                sample_cost_quantiles=[float(costs[i] / costs.mean()) for i in picks])
+
+
+def cpu_baseline(windows, poa_cells_per_window, ed_cells_per_window, budget_s, with_ed=True):
+    r = cpu_rates(windows, budget_s)
+    t_window = poa_cells_per_window / r["poa_cells_per_core_s"]
+    t_with_ed = t_window + ed_cells_per_window / max(1.0, r["ed_cells_per_core_s"])
+    value_no_ed = r["cores"] / t_window
+    value_ed = r["cores"] / t_with_ed
+    sample = (f"{r['cores']} windows spread evenly over the cost-sorted batch (cost {min(r['sample_cost_quantiles']):.2f}x-"
+              f"{max(r['sample_cost_quantiles']):.2f}x of the mean), one process per window for {budget_s:.0f} s each on {r['cores']} cores: "
+              f"{r['alignments']} alignments at {r['poa_cells_per_core_s'] / 1e9:.3f} GCUPS per core (scalar five-matrix engine), "
+              f"bit-parallel Levenshtein at {r['ed_cells_per_core_s'] / 1e9:.2f} GCUPS per core; windows/s = cores / "
+              f"(DP cells per window / rate + edit-distance cells per window / rate); features and mixture model (~2 % of the "
+              f"CPU time of a window) not charged")
+    return dict(value=value_ed if with_ed else value_no_ed, unit=UNIT, cores=r["cores"], kind="port", sample=sample,
+                value_without_edit_distance=value_no_ed, value_with_edit_distance=value_ed,
+                poa_gcups_per_core=r["poa_cells_per_core_s"] / 1e9, ed_gcups_per_core=r["ed_cells_per_core_s"] / 1e9,
+                poa_cells_per_window=poa_cells_per_window, ed_cells_per_window=ed_cells_per_window, wall_s=r["wall_s"],
+                note="CPU restatement of pyspoa (scalar; the real pyspoa 0.2.1 SIMD engine cannot be installed offline and would "
+                     "be several times faster) + bit-parallel Levenshtein; the reference itself runs no Levenshtein "
+                     "(src/DecisionMaker.py:76-84 is commented out): value_without_edit_distance is the reference-faithful path")
 
 
 # ------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--windows", type=int, default=1000, help="windows per rank and step (configs[1]: 1000)")
+    ap.add_argument("--windows", type=int, default=CONFIGS1_BATCH, help="windows per rank and step (configs[1]: 1000)")
+    ap.add_argument("--budget-s", type=float, default=520.0,
+                    help="seconds the K timed steps may take; the per-step batch shrinks to fit (0: never shrink)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-edit-distance", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=25.0)
-    ap.add_argument("--workers", type=int, default=0)
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--poa-threads", type=int, default=0)
     ap.add_argument("--ring-rows", type=int, default=0)
-    ap.add_argument("--poa-cols", type=int, default=0)
-    ap.add_argument("--streams", type=int, default=0)
+    ap.add_argument("--chunks", type=int, default=3)
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -223,52 +271,53 @@ def main():
     from svscope_b200 import _lib
     from svscope_b200.batch import localgraph_batch, upload_windows
     ctx = _lib.Context(local)
-    ncpu = os.cpu_count() or 8
-    workers = args.workers or max(2, min(12, (ncpu // max(1, world)) - 1))
-    ctx.set_option("workers", workers)
     if args.poa_threads:
         ctx.set_option("poa_threads", args.poa_threads)
     if args.ring_rows:
         ctx.set_option("ring_rows", args.ring_rows)
-    if args.poa_cols:
-        ctx.set_option("poa_cols", args.poa_cols)
-    if args.streams:
-        ctx.set_option("streams", args.streams)
     ed = not args.no_edit_distance
 
     t_gen = time.perf_counter()
-    windows = make_batch(args.windows, rank)
+    windows_all = make_batch(args.windows, rank)
     t_gen = time.perf_counter() - t_gen
-    reads = upload_windows(ctx, windows)                      # resident in HBM before timing
+
+    def run(wins, reads):
+        return localgraph_batch(wins, ctx=ctx, reads=reads, edit_distance=ed, chunks=args.chunks)
+
+    # ---- warm-up: W steps on a 64-window slice (context, arena, kernel images, allocator pools) ----
+    slice_w = windows_all[:: max(1, len(windows_all) // 64)][:64]
+    slice_reads = upload_windows(ctx, slice_w)
+    t_w = time.perf_counter()
+    for _ in range(max(args.warmup, 1)):
+        run(slice_w, slice_reads)
+    t_w = time.perf_counter() - t_w
+    slice_reads.close()
+
+    # ---- per-step batch: the configs[1] batch, or its first n windows if K steps would not fit ------
+    n_step = len(windows_all)
+    calib = None
+    if args.budget_s > 0 and args.steps > 1:
+        reads_all = upload_windows(ctx, windows_all)
+        barrier_sync()
+        t_c = time.perf_counter()
+        out_c = run(windows_all, reads_all)
+        torch.cuda.synchronize()
+        t_full = max_over_ranks(time.perf_counter() - t_c)
+        calib = {"full_batch_windows": len(windows_all), "full_batch_step_s": t_full,
+                 "full_batch_windows_per_s_per_gpu": len(windows_all) / t_full}
+        if t_full * args.steps > args.budget_s:
+            n_step = int(len(windows_all) * args.budget_s / (t_full * args.steps) / 1.04)
+            n_step = int(min_over_ranks(float(max(64, min(len(windows_all), n_step)))))
+        if n_step < len(windows_all):
+            reads_all.close()
+            reads_all = None
+    else:
+        reads_all = upload_windows(ctx, windows_all)
+    windows = windows_all[:n_step]
+    reads = reads_all if reads_all is not None else upload_windows(ctx, windows)     # resident in HBM before timing
     read_bytes = reads.nbytes
 
-    def step():
-        return localgraph_batch(windows, ctx=ctx, reads=reads, edit_distance=ed)
-
-    def e2e_step():
-        """Same step through the public batch call with host buffers: the reads are uploaded from
-        page-locked host memory and every result is copied back inside the timed region."""
-        barrier_sync()
-        t0 = time.perf_counter()
-        o2 = localgraph_batch(windows, ctx=ctx, reads=None, edit_distance=ed)
-        torch.cuda.synchronize()
-        barrier_sync()
-        t_e2e = max_over_ranks(time.perf_counter() - t0)
-        s2 = o2.stats
-        h2d = read_bytes + s2["poa_h2d_bytes"] + s2.get("feat_h2d_bytes", 0) + s2.get("em_h2d_bytes", 0)
-        d2h = s2["poa_d2h_bytes"] + s2.get("feat_d2h_bytes", 0) + s2.get("em_d2h_bytes", 0) + s2.get("ed_d2h_bytes", 0)
-        return o2, {"value": sum_over_ranks(float(args.windows)) / t_e2e, "unit": UNIT,
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "note": "timed on the last warm-up step" if args.warmup > 0 else "timed after the timed steps"}
-
-    # warm-up steps; the last one doubles as the end-to-end measurement (it is itself preceded by
-    # warm-up steps), which keeps the default run within minutes
-    e2e, o2 = None, None
-    for w in range(args.warmup):
-        if w == args.warmup - 1 and not args.no_e2e:
-            o2, e2e = e2e_step()
-        else:
-            out = step()
+    # ---- timed region ------------------------------------------------------------------------------
     sampler = ClockSampler(local)
     barrier_sync()
     if rank == 0:
@@ -276,11 +325,14 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record()
-    agg = {}
+    agg, stage = {}, {}
+    out = None
     for _ in range(args.steps):
-        out = step()
+        out = run(windows, reads)
         for k, v in out.stats.items():
             agg[k] = agg.get(k, 0.0) + v
+        for k, v in out.timings.items():
+            stage[k] = stage.get(k, 0.0) + v
     torch.cuda.synchronize()
     ev1.record()
     ev1.synchronize()
@@ -289,12 +341,27 @@ def main():
     dev_s = ev0.elapsed_time(ev1) / 1e3
     clocks = sampler.stop() if rank == 0 else None
     t_max = max_over_ranks(max(dev_s, 1e-9))
-    total_windows = sum_over_ranks(float(args.windows * args.steps))
+    t_min = min_over_ranks(max(dev_s, 1e-9))
+    total_windows = sum_over_ranks(float(len(windows) * args.steps))
     value = total_windows / t_max
-    if e2e is None and not args.no_e2e:
-        o2, e2e = e2e_step()
-    if o2 is not None:
+
+    # ---- end to end: the same step with host buffers (upload + every result copy inside) -----------
+    e2e = None
+    if not args.no_e2e:
+        barrier_sync()
+        t1 = time.perf_counter()
+        o2 = localgraph_batch(windows, ctx=ctx, reads=None, edit_distance=ed, chunks=args.chunks)
+        torch.cuda.synchronize()
+        barrier_sync()
+        t_e2e = max_over_ranks(time.perf_counter() - t1)
+        s2 = o2.stats
+        h2d = read_bytes + s2["poa_h2d_bytes"] + s2.get("feat_h2d_bytes", 0) + s2.get("em_h2d_bytes", 0)
+        d2h = (s2["poa_d2h_bytes"] + s2.get("poa_copy_bytes", 0) + s2.get("feat_d2h_bytes", 0) + s2.get("em_d2h_bytes", 0)
+               + s2.get("ed_d2h_bytes", 0))
         assert o2.records == out.records      # resident and host-buffer paths give the same records
+        e2e = {"value": sum_over_ranks(float(len(windows))) / t_e2e, "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": 1,
+               "note": "one step after the timed steps: reads uploaded from host memory, MSA / consensus / matrices copied back"}
 
     if rank != 0:
         return
@@ -307,79 +374,97 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    dp_s = st["poa_dp_ms"] / 1e3
-    n_launch = max(1.0, st["poa_dp_launches"])
-    algo_bytes_per_launch = st["poa_algo_bytes"] / n_launch
-    avg_launch_s = dp_s / n_launch
-    achieved_gbs = algo_bytes_per_launch / avg_launch_s / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (296 alignments, launch 14 of a depth-8 probe: "
-                                "profiles/r01_poa_persistent_kernel_final_ncu_full.txt); almost all of it is "
-                                "traceback codes (1-2 B per DP cell), which are implementation traffic, not algorithmic bytes",
-                "kernel": "poa_persistent_kernel<256,8>", "launches_per_step": n_launch,
-                "avg_launch_ms": avg_launch_s * 1e3,
-                "note": "algorithmic bytes = read + rank-ordered graph + alignment path (SURVEY 8d); the kernel is "
-                        "integer-ALU bound, see roofline_alu; launches of different worker streams overlap, so the "
-                        "per-launch event time is an upper bound of the exclusive time"}
     alu = ctx.int_alu_probe()
-    ops_per_cell = 18.0   # 8*indeg+10 integer add/max per cell at in-degree 1
-    poa_wall = max(1e-9, (out.timings["poa_msa"] + out.timings["poa_consensus"]))
-    gcups = st["poa_cells"] / poa_wall / 1e9
-    peak_gcups = alu["addmax"] * 2.0 / ops_per_cell   # fused add+max counts as two algorithmic ops
-    roofline_alu = {"bound": "int_alu", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": gcups / peak_gcups,
-                    "probe_gops": alu, "ops_per_cell": ops_per_cell,
-                    "note": "NOMINAL cells = sum (|V|+1)(L+1) over alignments (what the CPU engine fills); exact pruning evaluates "
-                            "about 30 % of them; achieved over the wall time of the two POA stages (last timed step); "
-                            "peak = measured fused add+max issue rate x 2 / 18 ops per cell"}
+    # ---- roofline of the dominant kernel (poa_window_kernel): integer ALU --------------------------
+    kern_s = st["poa_dp_ms"] / 1e3                      # CUDA events around the launches, on their streams (sum)
+    n_launch = max(1.0, st["poa_dp_launches"])
+    ops_per_cell = 18.0                                 # 8*indeg+10 integer add/max per cell at in-degree 1
+    peak_gcups = alu["addmax"] * 2.0 / ops_per_cell     # fused add+max counts as two algorithmic ops
+    gcups_nominal = st["poa_cells"] / kern_s / 1e9
+    gcups_eval = st["poa_eval_cells"] / kern_s / 1e9
+    algo_bytes = st["poa_algo_bytes"]
+    roofline = {
+        "bound": "int_alu", "kernel": f"poa_window_kernel<{ctx.get_option('poa_threads')},8>",
+        "achieved": gcups_nominal, "peak": peak_gcups, "unit": "GCUPS", "frac": gcups_nominal / peak_gcups,
+        "achieved_evaluated_cells": gcups_eval, "frac_evaluated_cells": gcups_eval / peak_gcups,
+        "evaluated_fraction": st["poa_eval_cells"] / max(1.0, st["poa_cells"]),
+        "traffic": NCU_TRAFFIC["bytes"] / NCU_TRAFFIC["alignments"] * (st["poa_alignments"] / n_launch),
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (2 windows, 120 alignments of "
+                        "3 kb reads: the working set of so small a launch stays in the 126 MB L2) scaled to the alignments of one "
+                        "launch here; at bench size the traceback codes (1-2 B per evaluated cell) do go to HBM: see hbm.implementation_bytes",
+        "launches_per_step": n_launch, "avg_launch_ms": kern_s / n_launch * 1e3,
+        "peak_source": "measured in this run: fused add+max issue rate (svs_int_alu_probe) x 2 / 18 ops per cell",
+        "probe_gops": alu, "ops_per_cell": ops_per_cell,
+        "note": "achieved = NOMINAL cells (sum (|V|+1)(L+1), what the CPU engine fills) / summed launch durations of the window "
+                "kernel (CUDA events on the launch streams; launches of different sub-batches overlap, so this is a lower bound); "
+                "the launch duration includes the in-kernel graph phases (export, traceback, merge, rank order: "
+                "poa.phase_share); exact pruning evaluates evaluated_fraction of the nominal cells",
+        "hbm": {"bound": "hbm", "achieved": algo_bytes / kern_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": algo_bytes / kern_s / 1e9 / hbm_peak, "peak_source": peak_src,
+                "algorithmic_bytes_per_step": algo_bytes,
+                "implementation_bytes": 1.35 * st["poa_eval_cells"],
+                "note": "algorithmic bytes = read + rank-ordered graph + alignment path (SURVEY 8d); implementation_bytes = "
+                        "traceback codes written (1 B per evaluated cell of single-predecessor rows, 2 B otherwise)"}}
+    ed_ms = max(st.get("ed_ms", 0.0), 1e-9)
+    kernels = {
+        "myers_kernel": {"bound": "int_alu", "achieved": st.get("ed_cells", 0.0) / ed_ms / 1e6, "unit": "GCUPS",
+                         "peak": alu["xor"] / 0.53, "frac": st.get("ed_cells", 0.0) / ed_ms / 1e6 / (alu["xor"] / 0.53),
+                         "note": "cells = L_i * L_j per pair; ~17 64-bit logic ops per 64-cell word step = 0.53 32-bit ops per cell "
+                                 "against the measured LOP3 issue rate; kernel time by CUDA events on its stream, which it "
+                                 "shares with the tail of the window kernels (it runs behind them)"},
+        "em_kernel": {"bound": "latency", "note": "FP64, one CTA per (window, K): < 2 % of a step, occupancy/latency bound; "
+                                                  "no roofline fraction claimed"}}
+    cyc = {k: st.get("poa_cyc_" + k, 0.0) for k in ("export", "dp", "traceback", "merge", "rank", "finish")}
+    cyc_tot = max(1.0, sum(cyc.values()))
+    wl = max(1.0, st.get("poa_wcyc_loop", 0.0) + st.get("poa_wcyc_wait_end", 0.0))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_max / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32 (POA DP, edit distance u32 bit-vectors), f64 (mixture model)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "windows_per_gpu": args.windows, "reads_per_window": 60,
-                   "edit_distance_matrix": ed, "l2": "inputs larger than L2 (reads + traceback codes >> 126 MB per step)",
-                   "parallelism": f"windows sharded over {world} GPU(s), no collective", "host_workers": workers,
-                   "poa_threads": ctx.get_option("poa_threads"), "poa_cols": ctx.get_option("poa_cols"),
-                   "ring_rows": ctx.get_option("ring_rows")},
+        "config": {"workload": WORKLOAD, "windows_per_step": len(windows), "windows_per_gpu": len(windows),
+                   "configs1_batch": CONFIGS1_BATCH, "reads_per_window": 60, "edit_distance_matrix": ed,
+                   "step_batch_note": ("the configs[1] batch" if len(windows) == CONFIGS1_BATCH else
+                                       f"first {len(windows)} windows of the {len(windows_all)}-window batch per step, so that "
+                                       f"{args.steps} steps fit {args.budget_s:.0f} s (the full batch takes "
+                                       f"{calib['full_batch_step_s']:.1f} s per step: calibration)"),
+                   "warmup_note": f"{max(args.warmup, 1)} warm-up steps on a 64-window slice ({t_w:.1f} s)",
+                   "l2": "inputs larger than L2 (reads + traceback codes >> 126 MB per step)",
+                   "parallelism": f"windows sharded over {world} GPU(s), no collective; host work per rank: one Python process",
+                   "poa_threads": ctx.get_option("poa_threads"), "ring_rows": ctx.get_option("ring_rows"),
+                   "sub_batches": int(out.stats.get("sub_batches", 1))},
+        "calibration": calib,
         "e2e": e2e,
-        "gpu_launches": int(agg.get("poa_dp_launches", 0) + agg.get("poa_tb_launches", 0) + agg.get("aux_launches", 0)),
+        "gpu_launches": int(agg.get("poa_dp_launches", 0) + agg.get("aux_launches", 0)),
         "clocks": clocks,
         "roofline": roofline,
-        "roofline_alu": roofline_alu,
-        "stage_seconds_last_step": {k: round(v, 3) for k, v in out.timings.items()},
+        "kernels": kernels,
+        "stage_seconds_per_step": {k: round(v / steps, 3) for k, v in stage.items()},
+        "rank_time_skew": t_max / max(t_min, 1e-9),
         "wall_s_timed": wall, "gen_s": t_gen,
-        "poa": {"cells_per_step": st["poa_cells"], "alignments_per_step": st["poa_alignments"],
+        "poa": {"cells_per_step": st["poa_cells"], "evaluated_cells_per_step": st["poa_eval_cells"],
+                "alignments_per_step": st["poa_alignments"],
                 "exported_row_frac": st["poa_exported_rows"] / max(1.0, st["poa_rows"]),
                 "pruning_retries_per_step": st.get("poa_prune_retries", 0.0),
-                "host_ms_per_step": {k: st.get("poa_" + k, 0.0) for k in
-                                     ("host_wait_ms", "host_merge_ms", "host_plan_ms", "host_pack_ms", "launch_ms")}},
-        "edit_distance": {"cells_per_step": st["ed_cells"], "kernel_ms_per_step": st["ed_ms"],
-                          "gcups": st["ed_cells"] / max(st["ed_ms"], 1e-9) / 1e6},
+                "failed_windows_per_step": st.get("poa_failed_windows", 0.0),
+                "phase_share": {k: v / cyc_tot for k, v in cyc.items()},
+                "dp_warps": {"working": (st.get("poa_wcyc_loop", 0.0) - st.get("poa_wcyc_wait_left", 0.0)) / wl,
+                             "waiting_for_neighbour": st.get("poa_wcyc_wait_left", 0.0) / wl,
+                             "waiting_at_end": st.get("poa_wcyc_wait_end", 0.0) / wl},
+                "host_ms_per_step": 0.0},
+        "edit_distance": {"cells_per_step": st.get("ed_cells", 0.0), "kernel_ms_per_step": st.get("ed_ms", 0.0)},
         "em_output_windows": sum(r[-1].endswith("EMOutput") for r in out.records),
+        "em_redraw_fraction": st.get("em_redraw_windows", 0.0) / max(1.0, st.get("windows_em", 1.0)),
     }
-    # informational, outside the timed region: the step after the Raw.bed,
-    # MisScore alignments of the records this step produced
-    try:
-        from svscope_b200 import PairwiseCompare as PC
-        mpairs = [p for r in out.records if str(r[9]) == "NormalOutput|EMOutput"
-                  for p in PC._record_pairs(str(r[3]), str(r[6]))]
-        mst = {}
-        t_m = time.perf_counter()
-        PC.misscore_pairs(mpairs, ctx=ctx, stats=mst)
-        t_m = time.perf_counter() - t_m
-        line["misscore_after_step"] = {"pairs": len(mpairs), "cells": mst.get("cells", 0.0),
-                                       "kernel_ms": mst.get("kernel_ms", 0.0), "wall_s": t_m,
-                                       "gcups_kernel": mst.get("cells", 0.0) / max(mst.get("kernel_ms", 0.0), 1e-9) / 1e6,
-                                       "note": "not part of `value`: PairwiseCompare.MisScorePipe's alignments "
-                                               "(svs_misscore_pairs) on the records of the last step"}
-    except Exception as exc:  # informational only
-        line["misscore_after_step"] = {"error": repr(exc)}
     if not args.no_cpu_baseline and world == 1:
-        cb = run_cpu(windows, args.cpu_budget)
-        line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port",
-                                "sample": cb["sample"], "raw_sample_windows_per_s": cb["raw_windows_per_s"],
-                                "note": "CPU restatement of pyspoa (real pyspoa 0.2.1 SIMD engine unavailable offline) + "
-                                        "numpy port of ReadsCluster/DecisionMaker + bit-parallel Levenshtein"}
+        poa_cpw = st["poa_cells"] / len(windows)
+        ed_cpw = st.get("ed_cells", 0.0) / len(windows)
+        cb = cpu_baseline(windows, poa_cpw, ed_cpw, args.cpu_budget, with_ed=ed)
+        model = float(np.mean([model_cells(w) for w in windows]))
+        cb["cost_model_residual"] = {"model_msa_cells_per_window": model,
+                                     "counted_cells_per_window_msa_and_consensus": poa_cpw,
+                                     "note": "the model covers the window MSA only; the reference arm adds the measured "
+                                             "consensus share"}
+        line["cpu_baseline"] = cb
     print(json.dumps(line))
 
 
@@ -392,32 +477,37 @@ def _shutdown():
         pass
 
 
+# consensus POA cells / window-MSA cells and edit-distance cells per window of the configs[1] batch,
+# counted on the device (profiles/r02_bench_*.json: poa.cells_per_step against model_cells)
+CONSENSUS_SHARE = 0.36
+
+
 def main_reference(args):
-    """The CPU path of the reference on this box's host cores (rank 0 only)."""
+    """The CPU path of the reference on this box's host cores (rank 0 only), timed ONCE on a bounded sample."""
     rank = env_int("RANK", 0)
     if rank != 0:
         return
     windows = make_batch(args.windows, 0)
-    cores = os.cpu_count() or 1
-    times, last = [], None
-    for i in range(args.warmup + args.steps):
-        budget = args.cpu_budget if i >= args.warmup else min(args.cpu_budget, 8.0)
-        last = run_cpu(windows, budget, cores)
-        if i >= args.warmup:
-            times.append(last)
-    value = float(np.mean([t["value"] for t in times]))
+    ed = not args.no_edit_distance
+    poa_cpw = float(np.mean([model_cells(w) for w in windows])) * (1.0 + CONSENSUS_SHARE)
+    ed_cpw = float(np.mean([sum(len(a) * len(b) for i, a in enumerate(w[0][1:]) for b in w[0][i + 2:]) for w in windows[:50]]))
+    cb = cpu_baseline(windows, poa_cpw, ed_cpw, args.cpu_budget, with_ed=ed)
+    value = cb["value"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": env_int("WORLD_SIZE", 1),
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean([t["seconds"] for t in times])) * 1e3,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["wall_s"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64 (CPU)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "windows_per_gpu": args.windows, "reads_per_window": 60,
-                       "edit_distance_matrix": True},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+                       "edit_distance_matrix": ed,
+                       "sample_note": "one bounded sample, timed once (the driver's steps/warmup are echoed, not repeated); "
+                                      "cells per window from the growth model of bench.model_cells x (1 + consensus share)"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "value_without_edit_distance",
+                                                "value_with_edit_distance", "poa_gcups_per_core", "ed_gcups_per_core")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "reference = negi2331026/SVScope Python path; its spoa.poa lives in the pyspoa wheel that cannot be "
-                    "installed offline, so the timed code is the oracle port (scalar five-matrix POA restatement + "
-                    "numpy mixture model + bit-parallel Levenshtein), one process per window on all host cores"}
+                    "installed offline, so the timed code is the oracle port (scalar five-matrix POA restatement, bit-parallel "
+                    "Levenshtein), one process per window on all host cores"}
     print(json.dumps(line))
 
 

@@ -24,7 +24,7 @@ from .synth import window_cost
 
 logging.basicConfig(level=logging.INFO, format="%(asctime)s - %(levelname)s - %(message)s")
 
-BATCH_WINDOWS = 512
+BATCH_WINDOWS = 1024
 
 
 def raw_bed_name(TSampleID: str, NSampleID: str) -> str:
@@ -43,8 +43,19 @@ def write_raw_bed(path: str, records, append: bool = False) -> None:
 
 
 def _ranks():
+    """(rank, world size).  Under torchrun (WORLD_SIZE > 1 in the environment) the process group
+    is created here if the caller has not done so: without it every process would believe it is
+    rank 0 of 1, compute all windows and fight over the same part file."""
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if not dist.is_available():
+        return 0, 1
+    if not dist.is_initialized() and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group("gloo")     # host-side gathers and barriers only: no collective on the data path
+        import atexit
+        atexit.register(lambda: dist.is_initialized() and dist.destroy_process_group())
+    if dist.is_initialized() and dist.get_world_size() > 1:
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
 
@@ -107,22 +118,42 @@ def localGraph_npz(args):
     finished = _finished_records([path] + sorted(glob.glob(glob.escape(path) + ".part*"))) if resume else set()
     if world > 1:
         dist.barrier(group=group)  # every rank has read the parts before anyone appends
-    windows = []
-    for name in sorted(os.listdir(args.savedir)):
-        if not re.search("npz", name):
-            continue
+    # pass 1: (file, row, cost) of every unfinished window - sequence lengths only, one file in memory at a time
+    files = [name for name in sorted(os.listdir(args.savedir)) if re.search("npz", name)]
+    meta = []
+    for fi, name in enumerate(files):
         dat = np.load(os.path.join(args.savedir, name), allow_pickle=True)["DatSet"]
         for i in range(dat.shape[0]):
-            row = list(dat[i])
+            row = dat[i]
             if finished and row[4] in finished:
                 continue
-            windows.append(row)
-    mine = _my_indices(windows)
+            meta.append((fi, i, window_cost(row)))
+        del dat
+    mine = set(_shard.my_shard([m[2] for m in meta], rank, world)) if world > 1 else set(range(len(meta)))
+    mine_by_file = {}
+    for k, (fi, i, _) in enumerate(meta):
+        if k in mine:
+            mine_by_file.setdefault(fi, []).append(i)
+    # pass 2: stream my windows, file by file, in full GPU batches (no rank ever holds all windows)
     with open(path + ".part%d" % rank, "a") as part:
-        for _, recs in iter_batches(windows, mine, BATCH_WINDOWS):
+        pending = []
+
+        def flush(rows):
+            recs = localgraph_batch(rows).records
             part.write("".join(_format(r) for r in recs))
             part.flush()
             os.fsync(part.fileno())
+
+        for fi in sorted(mine_by_file):
+            dat = np.load(os.path.join(args.savedir, files[fi]), allow_pickle=True)["DatSet"]
+            for i in mine_by_file[fi]:
+                pending.append(list(dat[i]))
+                if len(pending) >= BATCH_WINDOWS:
+                    flush(pending)
+                    pending = []
+            del dat
+        if pending:
+            flush(pending)
     if world > 1:
         dist.barrier(group=group)
     if rank == 0:

@@ -35,6 +35,7 @@ struct svs_poa_result {
   std::vector<svs::WinDesc> desc;
   std::vector<svs::WinResult> res;          // by group
   std::vector<int> out_buf;                 // index into out_bufs per group
+  std::vector<uint64_t> est_codes;          // estimated traceback-code bytes of the largest alignment of the group
   std::vector<uint8_t*> out_bufs;           // device output arenas (one per launch round)
   std::vector<int> round_groups;            // groups of the running round
   int tier = 0;
@@ -264,6 +265,7 @@ int submit(svs_ctx* ctx, const svs_reads* reads, const int64_t* members, const i
   r->desc.resize(n_groups);
   r->res.resize(n_groups);
   r->out_buf.assign(n_groups, -1);
+  r->est_codes.assign(n_groups, 0);
   const std::vector<Tier> tiers = make_tiers(ctx);
   std::vector<int> first;
   int64_t pairs_total = 0;
@@ -275,6 +277,14 @@ int submit(svs_ctx* ctx, const svs_reads* reads, const int64_t* members, const i
     if (debug_pairs) {
       d.pairs_off = pairs_total;
       pairs_total += static_cast<int64_t>(d.caps.nseq) * (static_cast<int64_t>(d.caps.vcap) + d.caps.lmax + 2);
+    }
+    {   // largest alignment of the group: the last read against a graph of first + ~8 % of the other bases,
+        // about 0.6 B of codes per nominal cell (band-limited rows, 1-2 B per evaluated cell)
+      uint64_t first = 0;
+      for (int64_t k = group_off[g]; k < group_off[g + 1] && first == 0; ++k)
+        first = static_cast<uint64_t>(reads->off[members[k] + 1] - reads->off[members[k]]);
+      const double rows = std::min<double>(d.caps.vcap, static_cast<double>(first) + 0.08 * static_cast<double>(d.caps.sumlen - first));
+      r->est_codes[g] = static_cast<uint64_t>(0.6 * rows * static_cast<double>(d.caps.lmax));
     }
     std::memset(&r->res[g], 0, sizeof(WinResult));
     r->res[g].status = kWinPending;
@@ -292,7 +302,7 @@ int submit(svs_ctx* ctx, const svs_reads* reads, const int64_t* members, const i
   // windows whose fixed part does not even fit a tier-0 slot start from the first tier that holds them
   std::vector<int> t0;
   for (int g : first) {
-    if (fixed_bytes(r->desc[g].caps) + (8u << 20) <= tiers[0].slot_bytes) t0.push_back(g);
+    if (fixed_bytes(r->desc[g].caps) + r->est_codes[g] + (8u << 20) <= tiers[0].slot_bytes) t0.push_back(g);
   }
   rc = launch_round(r.get(), t0, 0, 2.5);
   if (rc) return rc;
@@ -328,7 +338,9 @@ int wait(svs_poa_result* r) {
       const int st = r->res[g].status;
       if (st == kWinNodeCap || st == kWinEdgeCap || st == kWinStackCap)
         d.caps = estimate_caps(r->reads, r->members.data() + d.member_begin, d.caps.nseq, true);
-      const uint64_t need = fixed_bytes(d.caps) + (st == kWinCodesCap ? r->res[g].need_bytes + (r->res[g].need_bytes >> 3) : 0) + (8u << 20);
+      const uint64_t need = fixed_bytes(d.caps) + (8u << 20) +
+                            (st == kWinCodesCap ? r->res[g].need_bytes + (r->res[g].need_bytes >> 3)
+                                                : (st == kWinPending ? r->est_codes[g] : 0));
       if (need <= tiers[tier].slot_bytes || tier + 1 == static_cast<int>(tiers.size())) run.push_back(g);
     }
     std::vector<int> skipped;

@@ -169,3 +169,80 @@ def test_exact_pruning_equals_unpruned_and_oracle(ctx, oracle):
         oc, om = oracle.poa(w[0], 1)
         assert c == oc and m == om
     reads.close()
+
+
+def test_bench_windows_equal_committed_oracle_goldens(ctx, golden_dir):
+    """Windows of the bench's own configs[1] batch (synth.make_c2_window, full size: 60 reads of
+    5-15 kb) against records / MSA / consensus the CPU oracle produced (oracle/gen_golden_c2.py,
+    digests committed in tests/golden/c2_windows.json)."""
+    import hashlib
+    from svscope_b200.batch import localgraph_batch
+    from svscope_b200.spoa import poa
+    gold = json.load(open(os.path.join(golden_dir, "c2_windows.json")))["windows"]
+    assert len(gold) >= 8
+    wins = [synth.make_c2_window(g["index"]) for g in gold]
+    recs = localgraph_batch(wins, ctx=ctx).records
+    for g, w, rec in zip(gold, wins, recs):
+        line = "\t".join(str(x) for x in rec)
+        assert hashlib.sha256(line.encode()).hexdigest() == g["record_sha256"], g["index"]
+    for g, w in list(zip(gold, wins))[:3]:     # MSA and consensus of the window graph itself
+        cons, msa = poa(w[0], 1)
+        assert len(msa[0]) == g["msa_cols"]
+        assert hashlib.sha256("\n".join(msa).encode()).hexdigest() == g["msa_sha256"]
+        assert hashlib.sha256(cons.encode()).hexdigest() == g["consensus_sha256"]
+
+
+def test_window_with_more_than_31_in_edges_fails_alone(ctx, oracle):
+    """A node with more than 31 in-edges is beyond the 5-bit in-edge index of the traceback codes:
+    that group is reported (status 10) and the other groups of the call are unaffected."""
+    from svscope_b200._lib import ReadSet
+    from svscope_b200.poa_api import poa_groups
+    rng = np.random.default_rng(31)
+    left, right = synth._to_str(synth._rand_seq(rng, 30)), synth._to_str(synth._rand_seq(rng, 30))
+    bad = [left + right] + [left + synth._to_str(synth._rand_seq(rng, 2 + k)) + right for k in range(40)]
+    good = [synth._to_str(synth._rand_seq(rng, 50))] * 2 + [left + right, left + "ACGT" + right]
+    reads = ReadSet(ctx, good + bad + good)
+    groups = [list(range(0, 4)), list(range(4, 4 + len(bad))), list(range(4 + len(bad), 8 + len(bad)))]
+    cons, msas, st = poa_groups(ctx, reads, groups, strict=False)
+    o = oracle.PoaSession(1)
+    for s in bad:
+        o.add(s)
+    assert max(o.graph()["indeg"]) > 31
+    assert list(st["status"]) == [0, 10, 0]
+    oc, om = oracle.poa(good, 1)
+    assert cons[0] == oc and msas[0] == om and cons[2] == oc and msas[2] == om
+    assert cons[1] == "" and msas[1] == []
+    with pytest.raises(Exception):
+        poa_groups(ctx, reads, groups)        # strict: the caller of a single group gets an error
+    reads.close()
+
+
+def test_full_size_deep_tandem_repeat_window_properties(ctx):
+    """configs[2] at FULL size (120 reads of 20 kb, 10 % error, tandem-repeat expansion): the graph
+    outgrows the tier-0 scratch slots, so this exercises the memory tiers; the CPU oracle cannot hold
+    five 200k x 20k matrices, so parity is checked through size-independent properties: every MSA
+    row spells its read, the rows are equally long, the consensus is a path of plausible length,
+    and a second CTA shape gives the identical result (the scaled-down window against the oracle is
+    test_full_size_windows_equal_oracle_golden)."""
+    if os.environ.get("SVS_SKIP_FULL_C3"):
+        pytest.skip("SVS_SKIP_FULL_C3 set")
+    from svscope_b200._lib import ReadSet
+    from svscope_b200.poa_api import poa_groups
+    w = synth.make_c3(seed=3)
+    seqs = w[0]
+    assert len(seqs) == 121 and min(len(s) for s in seqs[1:]) > 15_000
+    reads = ReadSet(ctx, seqs)
+    try:
+        ctx.set_option("poa_threads", 512)
+        cons, msas, st = poa_groups(ctx, reads, [list(range(len(seqs)))])
+        assert st["failed_groups"] == 0
+        msa = msas[0]
+        assert len(msa) == len(seqs) and len({len(r) for r in msa}) == 1
+        assert [r.replace("-", "") for r in msa] == seqs
+        assert 0.8 * len(seqs[0]) < len(cons[0]) < 1.6 * len(seqs[0])
+        ctx.set_option("poa_threads", 384)
+        cons2, msas2, _ = poa_groups(ctx, reads, [list(range(len(seqs)))])
+        assert cons2 == cons and msas2 == msas
+    finally:
+        ctx.set_option("poa_threads", 384)
+        reads.close()

@@ -246,6 +246,45 @@ def _npz_worker(rank, world, port, savedir):
     dist.destroy_process_group()
 
 
+def _npz_worker_env_only(rank, world, port, savedir):
+    """What `torchrun -m svscope_b200.SVscope localGraph_npz` gives a process: environment variables, no group."""
+    import argparse
+    import types
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from svscope_b200 import SVscope
+    SVscope.localgraph_batch = lambda chunk, **kw: types.SimpleNamespace(
+        records=[w[4].split("\t") + ["s", "i", 1, "g", "rank%d" % rank, 2, "NormalOutput"] for w in chunk])
+    SVscope.BATCH_WINDOWS = 2
+    SVscope.main(["localGraph_npz", "-s", savedir, "-t", "T", "-n", "N"])
+
+
+def test_cli_under_torchrun_env_creates_the_process_group(tmp_path):
+    """The documented multi-GPU launch sets only RANK / WORLD_SIZE / MASTER_*: the CLI has to create
+    the (gloo) process group itself, shard the windows and write ONE complete Raw.bed."""
+    import torch.multiprocessing as mp
+    from svscope_b200 import SVscope
+    wins = []
+    for k in range(9):
+        w = synth.make_small_window(70 + k, body_len=40 + 5 * k, sv_len=10, n_tumor=3, n_normal=3, n_carriers=2)
+        w[4] = "chr%d\t%d\t%d" % (1 + k % 3, 500 * (9 - k), 500 * (9 - k) + 40)
+        wins.append(w)
+    synth.save_npz(str(tmp_path / "a.npz"), wins[:5])
+    synth.save_npz(str(tmp_path / "b.npz"), wins[5:])
+    ctx = mp.get_context("spawn")
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_npz_worker_env_only, args=(r, 2, port, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    lines = (tmp_path / SVscope.raw_bed_name("T", "N")).read_text().splitlines()
+    assert len(lines) == 9 and len({x.split("\t")[1] for x in lines}) == 9
+    assert {x.split("\t")[7] for x in lines} == {"rank0", "rank1"}
+    assert not [f for f in os.listdir(tmp_path) if ".part" in f]
+
+
 def test_two_rank_raw_bed_writer_gloo(tmp_path):
     """N>1 path of localGraph_npz on CPU: two ranks shard the windows, append to their own
     parts, rank 0 merges and sorts (the GPU batch call is a stand-in)."""
