@@ -199,7 +199,9 @@ def test_window_with_more_than_31_in_edges_fails_alone(ctx, oracle):
     from svscope_b200.poa_api import poa_groups
     rng = np.random.default_rng(31)
     left, right = synth._to_str(synth._rand_seq(rng, 30)), synth._to_str(synth._rand_seq(rng, 30))
-    bad = [left + right] + [left + synth._to_str(synth._rand_seq(rng, 2 + k)) + right for k in range(40)]
+    body = synth._to_str(synth._rand_seq(rng, 120))
+    # deletions of 1..45 bases that all end at the same position: that node collects an in-edge per length
+    bad = [body + right] + [body[:len(body) - k] + right for k in range(1, 46)]
     good = [synth._to_str(synth._rand_seq(rng, 50))] * 2 + [left + right, left + "ACGT" + right]
     reads = ReadSet(ctx, good + bad + good)
     groups = [list(range(0, 4)), list(range(4, 4 + len(bad))), list(range(4 + len(bad), 8 + len(bad)))]
