@@ -36,6 +36,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before any CUDA context (see svscope_b200/__init__.py)
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL would print its version on stdout, next to the JSON line
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "localGraph windows/sec"
 UNIT = "windows/s"
