@@ -88,6 +88,7 @@ struct WinMem {
   int32_t* depth;        // [vcap+1][4]
   int32_t* band;         // [vcap+1][2]
   uint32_t* coff;        // [vcap+3] code-row offsets of the running alignment
+  void* tbrow;           // [vcap+2] 32-byte traceback records of the running alignment (poa_dp2.cuh TbRow)
   int32_t* bnd;          // [2][4][vcap+1]
   int32_t* result;       // [4]
   int32_t* path;         // [2 * path_cap]
@@ -142,6 +143,7 @@ SVS_HD uint64_t win_layout(uint8_t* base, uint64_t slot_bytes, const WinCaps& c,
   m->depth = reinterpret_cast<int32_t*>(take(16 * V1));
   m->band = reinterpret_cast<int32_t*>(take(8 * V1));
   m->coff = reinterpret_cast<uint32_t*>(take(4 * (V1 + 2)));
+  m->tbrow = take(32 * V1);
   m->bnd = reinterpret_cast<int32_t*>(take(32 * V1));
   m->result = reinterpret_cast<int32_t*>(take(64));
   m->path_cap = static_cast<uint32_t>(V + c.lmax + 2);
@@ -592,8 +594,7 @@ SVS_HD void dg_export(X& x, const WinMem& m, const WinCaps& c, WinState* S, cons
     }
     for (uint32_t i = 1 + tid; i <= R; i += nt) {
       const uint32_t node = m.node_id[i];
-      uint32_t d = 0;
-      for (int32_t e = m.in_head[node]; e >= 0; e = m.e_next[e]) ++d;
+      const uint32_t d = m.indeg[node];
       m.pred_off[i + 1] = d ? d : 1;
       m.r_letter[i] = m.letter[node];
       m.r_flags[i] = m.has_out[node] ? 0 : kFlagSink;

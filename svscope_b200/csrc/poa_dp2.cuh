@@ -35,12 +35,22 @@ __host__ __device__ inline size_t dp2_smem_bytes(int threads, int ring_rows) {
          + static_cast<size_t>(nw) * kStageCap * 12;            // staged predecessor entries
 }
 
+struct __align__(16) TbRow {
+  uint32_t first_flags;   // first stored column - 1 (a multiple of 8) | bit 0: one predecessor, bit 1: chain row, bit 2: has cells
+  uint32_t coff;          // offset of the row's codes, units of 8 bytes
+  uint32_t pred_off;      // offset of the row's predecessor list
+  uint32_t pred0;         // first predecessor row
+  uint32_t ncols;         // stored cells
+  uint32_t node_id;
+  uint32_t pad0, pad1;
+};
+
 // Band, chunk range and code offset of every row.  band[2i], band[2i+1] = first / last
 // column (1-based; lo > hi: no cell); coff[i] = offset of the row's codes in units of 8 bytes.
 // Returns (in *need_bytes, written by thread 0 to shared memory by the caller) the total.
 template <int T>
 __device__ void compute_bands2(CtaExec& x, const PoaTask& tk, const Scores& s, int32_t lb, bool have_lb, int32_t* band,
-                               uint32_t* coff, unsigned long long* need_bytes) {
+                               uint32_t* coff, TbRow* tbrows, unsigned long long* need_bytes) {
   const int32_t L = static_cast<int32_t>(tk.L);
   for (uint32_t i = threadIdx.x; i <= tk.R; i += T) {
     int32_t lo = 1, hi = L;
@@ -81,6 +91,24 @@ __device__ void compute_bands2(CtaExec& x, const PoaTask& tk, const Scores& s, i
   __syncthreads();
   x.scan(coff + 1, tk.R + 1);     // coff[i+1] = units of rows 0..i  =>  coff[i] = offset of row i
   if (threadIdx.x == 0) *need_bytes = 8ull * coff[tk.R + 1] + 64;
+  // one record per row for the traceback walk
+  for (uint32_t i = threadIdx.x; i <= tk.R; i += T) {
+    TbRow r;
+    const int32_t lo = band[2 * i], hi = band[2 * i + 1];
+    const bool cells = i > 0 && lo <= hi;
+    const uint32_t po = tk.pred_off[i], npred = tk.pred_off[i + 1] - po;
+    r.first_flags = (cells ? ((static_cast<uint32_t>(lo - 1) >> 3) << 3) : 0u) | (npred == 1 ? 1u : 0u) |
+                    ((i > 0 && (tk.flags[i] & kFlagChain)) ? 2u : 0u) | (cells ? 4u : 0u);
+    r.coff = coff[i];
+    r.pred_off = po;
+    r.pred0 = (i > 0 && npred > 0) ? tk.preds[po] : 0u;
+    r.ncols = cells ? static_cast<uint32_t>((((hi - 1) >> 3) - ((lo - 1) >> 3) + 1) * 8) : 0u;
+    r.node_id = tk.node_id[i];
+    r.pad0 = 0; r.pad1 = 0;
+    int4* dst = reinterpret_cast<int4*>(tbrows + i);
+    dst[0] = make_int4(static_cast<int>(r.first_flags), static_cast<int>(r.coff), static_cast<int>(r.pred_off), static_cast<int>(r.pred0));
+    dst[1] = make_int4(static_cast<int>(r.ncols), static_cast<int>(r.node_id), 0, 0);
+  }
   __syncthreads();
 }
 
@@ -522,43 +550,69 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
   }
 }
 
-// Everything the traceback needs to read (band-limited code rows at 8 * coff[row]).
-struct TbView2 {
+// ---- traceback ---------------------------------------------------------------------------------
+// The walk is latency-bound: every step needs the row's code layout, the code itself and the
+// predecessor row.  All a step needs about a row sits in one 32-byte record (written by
+// compute_bands2), including the row's FIRST predecessor, so that
+//   * the usual step (move through in-edge 0) needs no look-up in the predecessor list, and
+//   * the record of that predecessor is requested before the code of the current cell arrives:
+//     in steady state a step costs one dependent global load (the code) instead of three.
+__device__ __forceinline__ TbRow tb_load(const TbRow* rows, uint32_t i) {
+  const int4 a = __ldcg(reinterpret_cast<const int4*>(rows + i));
+  const int4 b = __ldcg(reinterpret_cast<const int4*>(rows + i) + 1);
+  TbRow r;
+  r.first_flags = static_cast<uint32_t>(a.x); r.coff = static_cast<uint32_t>(a.y);
+  r.pred_off = static_cast<uint32_t>(a.z); r.pred0 = static_cast<uint32_t>(a.w);
+  r.ncols = static_cast<uint32_t>(b.x); r.node_id = static_cast<uint32_t>(b.y); r.pad0 = 0; r.pad1 = 0;
+  return r;
+}
+
+struct TbCtx {
   const uint8_t* codes;
-  const int32_t* band;
-  const uint32_t* coff;
+  const TbRow* rows;
   const uint16_t* col0code;
-  const uint32_t* pred_off;
   const uint32_t* preds;
-  const uint32_t* node_id;
 };
 
-__device__ __forceinline__ uint32_t tb2_code_at(const TbView2& v, const Scores& s, uint32_t ii, uint32_t jj) {
+__device__ __forceinline__ uint32_t tb3_code_at(const TbCtx& v, const Scores& s, const TbRow& R, uint32_t ii, uint32_t jj) {
   if (ii == 0) return jj == 0 ? 0u : row0_code(s, static_cast<int32_t>(jj));
   if (jj == 0) return v.col0code[ii];
-  const uint32_t first = (static_cast<uint32_t>(v.band[2 * ii] - 1) >> 3) << 3;   // first stored column - 1
-  const uint8_t* row = v.codes + 8ull * v.coff[ii];
-  const uint32_t col = jj - 1 - first;
-  if (v.pred_off[ii + 1] - v.pred_off[ii] == 1) return row[col];
+  const uint8_t* row = v.codes + 8ull * R.coff;
+  const uint32_t col = jj - 1 - (R.first_flags & ~7u);
+  if (R.first_flags & 1u) return row[col];
   return reinterpret_cast<const uint16_t*>(row)[col];
 }
 
-// One iteration of the reference's traceback loop at (i, j) != (0, 0) (same decisions as
-// poa_cell.h tb_step, code rows addressed through coff).
-__device__ bool tb2_step(const TbView2& v, const Scores& s, uint32_t& i, uint32_t& j, int32_t& n, int32_t* out_pairs,
-                         int32_t cap) {
-  auto pred_row = [&](uint32_t ii, uint32_t k) -> uint32_t { return k == kNoPred ? 0u : v.preds[v.pred_off[ii] + k]; };
-  const uint32_t cd = tb2_code_at(v, s, i, j);
+__device__ __forceinline__ uint32_t tb3_pred_row(const TbCtx& v, const TbRow& R, uint32_t k) {
+  if (k == kNoPred) return 0u;
+  if (k == 0) return R.pred0;
+  return v.preds[R.pred_off + k];
+}
+
+// Moves the walk from row `i` (record cur, speculative record spec of cur.pred0) to row `to`.
+__device__ __forceinline__ void tb3_goto(const TbCtx& v, uint32_t& i, TbRow& cur, TbRow& spec, uint32_t to) {
+  if (to == i) return;
+  if (to == 0) { i = 0; return; }
+  cur = (to == cur.pred0) ? spec : tb_load(v.rows, to);
+  i = to;
+  if (cur.pred0 != 0) spec = tb_load(v.rows, cur.pred0);   // requested now, needed at the next row change
+}
+
+// One iteration of the reference's traceback loop at (i, j) != (0, 0): same decisions as poa_cell.h tb_step.
+__device__ bool tb3_step(const TbCtx& v, const Scores& s, uint32_t& i, uint32_t& j, TbRow& cur, TbRow& spec, int32_t& n,
+                         int32_t* out_pairs, int32_t cap) {
+  const uint32_t cd = tb3_code_at(v, s, cur, i, j);
   const uint32_t move = cd & 3, ext = (cd >> 2) & 1, km = (cd >> 5) & 31;
   uint32_t pi, pj;
-  if (move == kMoveDiag) { pi = pred_row(i, km); pj = j - 1; }
-  else if (move == kMoveVert) { pi = pred_row(i, km); pj = j; }
+  if (move == kMoveDiag) { pi = tb3_pred_row(v, cur, km); pj = j - 1; }
+  else if (move == kMoveVert) { pi = tb3_pred_row(v, cur, km); pj = j; }
   else { pi = i; pj = j - 1; }
   if (n >= cap) return false;
-  out_pairs[2 * n] = (i == pi) ? -1 : static_cast<int32_t>(v.node_id[i]);
+  out_pairs[2 * n] = (i == pi) ? -1 : static_cast<int32_t>(cur.node_id);
   out_pairs[2 * n + 1] = (j == pj) ? -1 : static_cast<int32_t>(j - 1);
   ++n;
-  i = pi; j = pj;
+  tb3_goto(v, i, cur, spec, pi);
+  j = pj;
   if (move == kMoveHorz && ext) {
     while (true) {
       if (n >= cap) return false;
@@ -566,68 +620,76 @@ __device__ bool tb2_step(const TbView2& v, const Scores& s, uint32_t& i, uint32_
       out_pairs[2 * n + 1] = static_cast<int32_t>(j - 1);
       ++n;
       --j;
-      if (j == 0 || !((tb2_code_at(v, s, i, j) >> 3) & 1)) break;
+      if (j == 0 || !((tb3_code_at(v, s, cur, i, j) >> 3) & 1)) break;
     }
   } else if (move == kMoveVert && ext) {
     while (i != 0) {
-      const uint32_t c2 = tb2_code_at(v, s, i, j);
+      const uint32_t c2 = tb3_code_at(v, s, cur, i, j);
       const uint32_t stop = (c2 >> 4) & 1, ku = (c2 >> 10) & 31;
-      const uint32_t up = pred_row(i, ku);
+      const uint32_t up = tb3_pred_row(v, cur, ku);
       if (n >= cap) return false;
-      out_pairs[2 * n] = static_cast<int32_t>(v.node_id[i]);
+      out_pairs[2 * n] = static_cast<int32_t>(cur.node_id);
       out_pairs[2 * n + 1] = -1;
       ++n;
-      i = up;
+      tb3_goto(v, i, cur, spec, up);
       if (stop || i == 0) break;
     }
   }
   return true;
 }
 
-// Traceback by one warp: the 32 lanes test the cells (i-k, j-k) for "chain row + diagonal move"
-// and the walk advances by the number of leading hits; anything else is one serial step.
-__device__ void tb2_walk_warp(const PoaTask& tk, const Scores& s, const int32_t* band, const uint32_t* coff) {
-  const TbView2 v{tk.codes, band, coff, tk.col0code, tk.pred_off, tk.preds, tk.node_id};
+// Traceback by one warp.  While the walk is on a chain row the 32 lanes test the cells (i-k, j-k)
+// for "chain row + diagonal move" and the walk advances by the number of leading hits; anything
+// else is one serial step (every lane executes it on identical values, lane 0 stores).
+__device__ void tb3_walk_warp(const PoaTask& tk, const Scores& s, const TbRow* rows) {
+  const TbCtx v{tk.codes, rows, tk.col0code, tk.preds};
   const int lane = threadIdx.x & 31;
   uint32_t i = static_cast<uint32_t>(tk.result[0]), j = tk.L;
   int32_t n = 0;
   const int32_t cap = static_cast<int32_t>(tk.path_cap);
   bool ok = true;
+  TbRow cur = tb_load(rows, i), spec = cur;
+  if (i != 0 && cur.pred0 != 0) spec = tb_load(rows, cur.pred0);
+  int32_t* path = tk.path;
   while (ok && !(i == 0 && j == 0)) {
-    bool mine = false;
-    int32_t node = 0;
-    if (i > static_cast<uint32_t>(lane) && j > static_cast<uint32_t>(lane)) {
-      const uint32_t r = i - lane, c = j - lane;
-      const int32_t blo = band[2 * r], bhi = band[2 * r + 1];
-      const uint32_t first = blo >= 1 ? ((static_cast<uint32_t>(blo - 1) >> 3) << 3) : 0u;
-      const uint32_t lastc = blo <= bhi ? ((((static_cast<uint32_t>(bhi - 1)) >> 3) << 3) + 8) : 0u;   // one past the last stored column - 1
-      const bool inside = blo <= bhi && c - 1 >= first && c - 1 < lastc;
-      if (inside && (tk.flags[r] & kFlagChain)) {
-        const uint32_t cd = tk.codes[8ull * coff[r] + (c - 1 - first)];
-        if ((cd & 3u) == kMoveDiag) {
-          mine = true;
-          node = static_cast<int32_t>(tk.node_id[r]);
+    int run = 0;
+    if (i != 0 && (cur.first_flags & 2u)) {   // chain row: try a diagonal run
+      bool mine = false;
+      int32_t node = 0;
+      if (i > static_cast<uint32_t>(lane) && j > static_cast<uint32_t>(lane)) {
+        const uint32_t r = i - lane, c = j - lane;
+        const TbRow R = lane == 0 ? cur : tb_load(rows, r);
+        const uint32_t first = R.first_flags & ~7u;
+        const bool inside = (R.first_flags & 4u) && c - 1 >= first && c - 1 < first + R.ncols;
+        if (inside && (R.first_flags & 2u)) {
+          const uint32_t cd = tk.codes[8ull * R.coff + (c - 1 - first)];
+          if ((cd & 3u) == kMoveDiag) {
+            mine = true;
+            node = static_cast<int32_t>(R.node_id);
+          }
+        }
+      }
+      const unsigned hit = __ballot_sync(0xffffffffu, mine);
+      const int m = __ffs(~hit) - 1;
+      run = m < 0 ? 32 : m;
+      if (run > 0) {
+        if (n + run > cap) { ok = false; break; }
+        if (lane < run) {
+          path[2 * (n + lane)] = node;
+          path[2 * (n + lane) + 1] = static_cast<int32_t>(j - lane - 1);
+        }
+        n += run;
+        i -= run;
+        j -= run;
+        if (i != 0) {
+          cur = tb_load(rows, i);
+          if (cur.pred0 != 0) spec = tb_load(rows, cur.pred0);
         }
       }
     }
-    const unsigned hit = __ballot_sync(0xffffffffu, mine);
-    const int m = __ffs(~hit) - 1;
-    const int run = m < 0 ? 32 : m;
-    if (run > 0) {
-      if (n + run > cap) { ok = false; break; }
-      if (lane < run) {
-        tk.path[2 * (n + lane)] = node;
-        tk.path[2 * (n + lane) + 1] = static_cast<int32_t>(j - lane - 1);
-      }
-      n += run;
-      i -= run;
-      j -= run;
-    } else {
-      if (lane == 0) ok = tb2_step(v, s, i, j, n, tk.path, cap);
-      i = __shfl_sync(0xffffffffu, i, 0);
-      j = __shfl_sync(0xffffffffu, j, 0);
-      n = __shfl_sync(0xffffffffu, n, 0);
-      ok = __shfl_sync(0xffffffffu, static_cast<int>(ok), 0) != 0;
+    if (run == 0) {
+      // every lane walks the same step on the same values (uniform loads); only lane 0 stores
+      ok = tb3_step(v, s, i, j, cur, spec, n, path, cap);
     }
   }
   if (lane == 0) tk.result[2] = ok ? n : -1;

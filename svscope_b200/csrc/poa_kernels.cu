@@ -288,7 +288,7 @@ poa_window_kernel(const WinParams P) {
         bool have_lb = tk.prune != 0;
         for (int attempt = 0; attempt < 3; ++attempt) {
           if (tid == 0) { tk.result[0] = 0; tk.result[1] = INT32_MIN; }
-          compute_bands2<T>(x, tk, s, lb, have_lb, m.band, m.coff, &s_need2);
+          compute_bands2<T>(x, tk, s, lb, have_lb, m.band, m.coff, static_cast<TbRow*>(m.tbrow), &s_need2);
           if (s_need2 > tk.codes_cap) { v2_overflow = true; break; }
           dp2_align<T>(tk, s, P.tabs, P.ring_rows, smem_raw, m.band, m.coff, s_eval);
           const int32_t found_row = tk.result[0], found = tk.result[1];
@@ -305,7 +305,7 @@ poa_window_kernel(const WinParams P) {
         }
       }
       long long t1 = clock64();
-      if (tid < 32) tb2_walk_warp(tk, s, m.band, m.coff);
+      if (tid < 32) tb3_walk_warp(tk, s, static_cast<const TbRow*>(m.tbrow));
       __syncthreads();
       long long t2 = clock64();
       if (tid == 0) {
