@@ -132,22 +132,32 @@ struct CtaExec {
       }
     }
     if (warp == (nw > 1 ? 1u : 0u)) {
-      int32_t* ring = sweep_ring + 128;                 // [64][2] partial (smin, smax) of rows [i-63, i]
+      // ring slot of row r: what successors less than 64 rows away found; successors further away wrote
+      // to global memory, and they are all done before the 32-row batch of r starts, so that part is
+      // fetched per batch (one row per lane) and joined when the row is finalised
+      int32_t* ring = sweep_ring + 128;                 // [64][2]
       for (uint32_t k = lane; k < 64; k += 32) { ring[2 * k] = INT32_MAX; ring[2 * k + 1] = -1; }
       __syncwarp();
       for (uint32_t i1 = R; i1 >= 1; i1 -= min(i1, 32u)) {
-        // rows i1, i1-1, ... (up to 32), lane l holds the predecessor range of row i1 - l
+        // rows i1, i1-1, ... (up to 32), lane l holds the predecessor range and the far part of row i1 - l
         const uint32_t nrows = min(32u, i1);
         const uint32_t pb = lane < nrows ? m.pred_off[i1 - lane] : 0;
         const uint32_t pe = lane < nrows ? m.pred_off[i1 - lane + 1] : 0;
+        const int32_t far_lo = lane < nrows ? dp[4 * (i1 - lane) + 2] : INT32_MAX;
+        const int32_t far_hi = lane < nrows ? dp[4 * (i1 - lane) + 3] : -1;
         for (uint32_t r = 0; r < nrows; ++r) {
           const uint32_t i = i1 - r;
           const uint32_t b = __shfl_sync(0xffffffffu, pb, r), e = __shfl_sync(0xffffffffu, pe, r);
-          int32_t lo = ring[2 * (i & 63)], hi = ring[2 * (i & 63) + 1];
+          int32_t lo = min(ring[2 * (i & 63)], __shfl_sync(0xffffffffu, far_lo, r));
+          int32_t hi = max(ring[2 * (i & 63) + 1], __shfl_sync(0xffffffffu, far_hi, r));
           if (lo == INT32_MAX) { lo = 0; hi = 0; }   // no successor
           const int32_t a = lo + 1, c = hi + 1;
           __syncwarp();
-          if (lane == 0) { dp[4 * i + 2] = lo; dp[4 * i + 3] = hi; }
+          if (lane == 0) {
+            dp[4 * i + 2] = lo; dp[4 * i + 3] = hi;
+            ring[2 * (i & 63)] = INT32_MAX; ring[2 * (i & 63) + 1] = -1;   // the slot is free for row i - 64
+          }
+          __syncwarp();
           for (uint32_t k = b + lane; k < e; k += 32) {   // the predecessors of a row are distinct rows
             const uint32_t p = m.preds[k];
             if (p == 0) continue;
@@ -159,9 +169,6 @@ struct CtaExec {
               dp[4 * p + 3] = max(dp[4 * p + 3], c);
             }
           }
-          __syncwarp();
-          // the slot now belongs to row i - 64: start from what successors 64 or more rows away left for it
-          if (lane == 0 && i > 64) { ring[2 * (i & 63)] = dp[4 * (i - 64) + 2]; ring[2 * (i & 63) + 1] = dp[4 * (i - 64) + 3]; }
           __syncwarp();
         }
         if (i1 <= 32) break;
