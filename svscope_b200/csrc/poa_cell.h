@@ -99,44 +99,54 @@ struct RowCarry {
   int32_t A, E, Q, H;
 };
 
-// ---- fast path for rows with a single predecessor (most rows) --------------------------------
-// With one predecessor every in-edge index is 0 and the vertical candidates depend on the
-// predecessor only through H and the five low bits (dF, dO) of its packed word:
-//   F = H + g + max(0, (e-g) - dF),  O = H + q + max(0, (c-q) - dO),
-// and the two flags taken at the predecessor (xV: a vertical move is an extension, sF: the F
-// maximum is the gap open) are pure functions of (dF, dO): 32-entry truth tables.
-struct SingleTables {
-  uint32_t xv_mask;   // bit (dF*8+dO): vertical move would be a gap extension
-  uint32_t sf_mask;   // bit (dF*8+dO): H+g attains F (stop flag of the extension walk)
-  uint32_t so_mask;   // bit (dF*8+dO): H+q attains O
+// ---- what a successor reads from a predecessor's packed word -----------------------------------
+// The vertical candidates depend on the predecessor only through H and the five low bits
+// (low = dF*8+dO) of its packed word:
+//   F = H + max(g, e - dF),   O = H + max(q, c - dO),
+// and the flags taken at the predecessor (xV: a vertical move is an extension, sF / sO: the gap
+// open attains the F / O maximum, i.e. the extension walk stops there) are pure functions of low.
+// All of it comes from a 32-entry table indexed by low.  On the device lane l of a warp holds
+// entry l in registers and a look-up is ONE warp shuffle whose source lane is the packed word
+// itself (the shuffle uses its five low bits): no field extraction in the row loop.
+struct PredLutEntry {
+  // rows with several predecessors ("key" form, see below): key of in-edge k = 2*w + 2*(31-k) + t*
+  int32_t tf, to, tv;
+  // rows with one predecessor: F = H + sf, O = H + so, sm = xV | sF << 1
+  int32_t sf, so, sm;
 };
 
-SVS_HD SingleTables make_single_tables(const Scores& s) {
-  SingleTables t{0u, 0u, 0u};
-  for (int low = 0; low < 32; ++low) {
-    const int32_t dF = (low >> 3) & 3, dO = low & 7;
-    const int32_t G = s.g, Fe = -dF + s.e, Oq = s.q, Oe = -dO + s.c;
-    const int32_t V = imax(imax(G, Fe), imax(Oq, Oe));
-    if ((Fe == V) || (G != V && Oe == V)) t.xv_mask |= 1u << low;
-    if (G >= Fe) t.sf_mask |= 1u << low;
-    if (Oq >= Oe) t.so_mask |= 1u << low;
-  }
+SVS_HD PredLutEntry pred_lut_entry(const Scores& s, int32_t low) {
+  const int32_t dF = (low >> 3) & 3, dO = low & 7;
+  const int32_t G = s.g, Fe = -dF + s.e, Oq = s.q, Oe = -dO + s.c;
+  const int32_t Fc = imax(G, Fe), Oc = imax(Oq, Oe), V = imax(Fc, Oc);
+  const int32_t xv = ((Fe == V) || (G != V && Oe == V)) ? 1 : 0;
+  const int32_t sf = (G >= Fe) ? 1 : 0, so = (Oq >= Oe) ? 1 : 0;
+  PredLutEntry t;
+  t.tf = Fc * 64 + sf - 2 * low;
+  t.to = Oc * 64 + so - 2 * low;
+  t.tv = V * 64 + xv - 2 * low;
+  t.sf = Fc;
+  t.so = Oc;
+  t.sm = xv | (sf << 1);
   return t;
 }
 
-// Result: a.Fm, a.Om, a.D as in the general path; a.meta = xV | sF << 1.
-SVS_HD void cell_pred_single(CellAcc& a, int32_t w, int32_t Hpl, int32_t sub, const Scores& s,
-                             const SingleTables& t) {
+// ---- fast path for rows with a single predecessor (most rows) --------------------------------
+// w = packed word of the predecessor in this column, Hpl = its H in the column on the left,
+// (sfv, sov, smv) = table entry of w.  Result: a.Fm, a.Om, a.D = the F, O and diagonal candidates,
+// a.meta = xV | sF << 1.
+SVS_HD void cell_pred_single(CellAcc& a, int32_t w, int32_t Hpl, int32_t sub, int32_t sfv, int32_t sov, int32_t smv) {
   const int32_t Hp = w >> 5;
-  const int32_t dF = (w >> 3) & 3, dO = w & 7;
-  a.Fm = Hp + s.g + imax((s.e - s.g) - dF, 0);
-  a.Om = Hp + s.q + imax((s.c - s.q) - dO, 0);
+  a.Fm = Hp + sfv;
+  a.Om = Hp + sov;
   a.D = Hpl + sub;
-  const uint32_t low = static_cast<uint32_t>(w) & 31u;
-  a.meta = ((t.xv_mask >> low) & 1u) | (((t.sf_mask >> low) & 1u) << 1);
+  a.meta = static_cast<uint32_t>(smv);
 }
 
 // Completes a single-predecessor cell; returns the low byte of the code (indices are 0).
+// Cells outside a pruning band carry kNegBand and whatever is derived from them stays below every
+// real score (|real| < 2^21 while pruning is on, kNegBand = -2^22, drift per row / column < 16):
+// no clamping is needed, decisions of cells on a co-optimal path never involve such values.
 SVS_HD uint32_t cell_finish_single(const CellAcc& a, RowCarry& cy, const Scores& s, int32_t& H_out) {
   const int32_t eo = cy.A + s.g, ee = cy.E + s.e, qo = cy.A + s.q, qe = cy.Q + s.c;
   const int32_t E = imax(eo, ee), Q = imax(qo, qe);
@@ -157,41 +167,39 @@ SVS_HD uint32_t cell_finish_single(const CellAcc& a, RowCarry& cy, const Scores&
 // A candidate value v of in-edge k with flag f is folded as the single integer
 //   key = v*64 + (31-k)*2 + f ,
 // so that one max() keeps the largest value, among equal values the smallest in-edge index,
-// and carries the flag of that in-edge along (|v| < 2^24 is checked on the host).
+// and carries the flag of that in-edge along (|v| < 2^24 is checked before the alignment starts).
+// With v = H + (table value) and the packed word w = H*32 + low:  key = 2*w + 2*(31-k) + t[low].
+// The diagonal candidates differ between in-edges only by H of the left column, so their key is
+//   (wl & ~31) | (31-k) = H_left*32 + (31-k);  the substitution score is added once per cell
+// after the fold (cell_key_add_sub).
 // CellAcc is reused: Fm = key of F, Om = key of O, D = key of the diagonal, meta = key of V.
 constexpr int64_t kMaxKeySpan = 1 << 24;
 
-SVS_HD void cell_pred_key(CellAcc& a, uint32_t k, int32_t w, int32_t Hpl, int32_t sub, const Scores& s,
-                          const SingleTables& t) {
-  const int32_t Hp = w >> 5;
-  const int32_t dF = (w >> 3) & 3, dO = w & 7;
-  const uint32_t low = static_cast<uint32_t>(w) & 31u;
-  const int32_t Fc = Hp + s.g + imax((s.e - s.g) - dF, 0);
-  const int32_t Oc = Hp + s.q + imax((s.c - s.q) - dO, 0);
-  const int32_t Vk = imax(Fc, Oc);
-  const int32_t Dk = Hpl + sub;
-  const int32_t base = static_cast<int32_t>(31u - k) * 2;
-  const int32_t kf = Fc * 64 + base + static_cast<int32_t>((t.sf_mask >> low) & 1u);
-  const int32_t ko = Oc * 64 + base + static_cast<int32_t>((t.so_mask >> low) & 1u);
-  const int32_t kv = Vk * 64 + base + static_cast<int32_t>((t.xv_mask >> low) & 1u);
-  const int32_t kd = Dk * 64 + base;
-  if (k == 0) {
-    a.Fm = kf; a.Om = ko; a.D = kd; a.meta = static_cast<uint32_t>(kv);
-  } else {
-    a.Fm = imax(a.Fm, kf);
-    a.Om = imax(a.Om, ko);
-    a.D = imax(a.D, kd);
-    a.meta = static_cast<uint32_t>(imax(static_cast<int32_t>(a.meta), kv));
-  }
+SVS_HD void cell_key_init(CellAcc& a) {
+  a.Fm = INT32_MIN; a.Om = INT32_MIN; a.D = INT32_MIN; a.meta = static_cast<uint32_t>(INT32_MIN);
 }
+
+// rk = 31 - k;  w, wl = packed words of in-edge k in this column / the column on the left;
+// (tfv, tov, tvv) = table entry of w
+SVS_HD void cell_pred_key(CellAcc& a, int32_t rk, int32_t w, int32_t wl, int32_t tfv, int32_t tov, int32_t tvv) {
+  const int32_t t = 2 * w + 2 * rk;
+  a.Fm = imax(a.Fm, t + tfv);
+  a.Om = imax(a.Om, t + tov);
+  a.meta = static_cast<uint32_t>(imax(static_cast<int32_t>(a.meta), t + tvv));
+  a.D = imax(a.D, (wl & ~31) | rk);
+}
+
+// after the last in-edge: the diagonal key becomes (H_left + sub)*32 + (31-k)
+SVS_HD void cell_key_add_sub(CellAcc& a, int32_t sub) { a.D += sub * 32; }
 
 // value of the cell state a successor needs (for packing / the scan)
 SVS_HD int32_t key_value(int32_t key) { return key >> 6; }
+SVS_HD int32_t key_value_diag(int32_t key) { return key >> 5; }
 
 SVS_HD uint16_t cell_finish_key(const CellAcc& a, RowCarry& cy, const Scores& s, int32_t& H_out,
                                 int32_t& F_out, int32_t& O_out) {
   const int32_t kV = static_cast<int32_t>(a.meta);
-  const int32_t Fm = a.Fm >> 6, Om = a.Om >> 6, D = a.D >> 6, V = kV >> 6;
+  const int32_t Fm = a.Fm >> 6, Om = a.Om >> 6, D = a.D >> 5, V = kV >> 6;
   const int32_t eo = cy.A + s.g, ee = cy.E + s.e, qo = cy.A + s.q, qe = cy.Q + s.c;
   const int32_t E = imax(eo, ee), Q = imax(qo, qe);
   const int32_t A = imax(D, V);
@@ -200,7 +208,7 @@ SVS_HD uint16_t cell_finish_key(const CellAcc& a, RowCarry& cy, const Scores& s,
   const uint32_t hx = (ee == H) || (cy.H + s.g != H && qe == H);
   const uint32_t move = is_d ? kMoveDiag : (is_v ? kMoveVert : kMoveHorz);
   const uint32_t ext = is_d ? 0u : (is_v ? static_cast<uint32_t>(kV & 1) : hx);
-  const uint32_t km = is_d ? 31u - ((static_cast<uint32_t>(a.D) >> 1) & 31u)
+  const uint32_t km = is_d ? 31u - (static_cast<uint32_t>(a.D) & 31u)
                            : (is_v ? 31u - ((static_cast<uint32_t>(kV) >> 1) & 31u) : 0u);
   const uint32_t lcnext = (E + s.e >= A + s.g) || (Q + s.c >= A + s.q);
   // vertical-extension walk: first in-edge attaining F or O (F wins ties)

@@ -183,13 +183,16 @@ __device__ __noinline__ bool dp2_stage_preds(const PoaTask& tk, const int32_t* b
 }
 
 template <int T>
-__device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, const SingleTables& tabs, const int ring_rows,
+__device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, const int ring_rows,
                                           unsigned char* smem_raw, const int32_t* __restrict__ band,
                                           const uint32_t* __restrict__ coff, unsigned long long* eval_chunks) {
   constexpr int kC = 8;
   constexpr int NW = T / 32;
   const int32_t NEGW = pack_cell(kNegBand, kNeg, kNeg);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // entry `lane` of the table a successor looks up by the five low bits of a predecessor's packed word
+  // (poa_cell.h): a look-up is one shuffle whose source lane is the packed word itself
+  const PredLutEntry lut = pred_lut_entry(s, lane);
   // per warp: ring_rows packed rows (row r in slot r % ring_rows), slot ring_rows = the virtual source row
   // in my columns, slot ring_rows + 1 = scratch for a predecessor row fetched from global memory: every
   // predecessor is read from shared memory by ONE copy of the cell code
@@ -348,9 +351,13 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
         }
 
         // ---- phase 1: fold predecessor rows ---------------------------------------------------
+        // Executed by every lane of the warp (the table look-ups are shuffles); lanes without a cell
+        // in this row fold band-edge values that nothing reads.
         CellAcc acc[kC];
+        if (!single) {
 #pragma unroll
-        for (int c = 0; c < kC; ++c) { acc[c].Fm = 0; acc[c].Om = 0; acc[c].D = 0; acc[c].meta = 0; }
+          for (int c = 0; c < kC; ++c) cell_key_init(acc[c]);
+        }
         for (uint32_t e = nb; e < ne; ++e) {
           const int32_t src = psrc[e];
           const uint32_t chk = pchk[e];
@@ -380,25 +387,32 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
 #pragma unroll
             for (int c = 0; c < kC; ++c) w[c] = NEGW;
           }
-          int32_t hl = (lane == 0) ? hl0 : (left_ok ? unpack_h(row[kC * lane - 1]) : kNegBand);
-          if (t_active) {
-            // ONE copy of the cell code for every row (rows with a single predecessor fold it as in-edge 0):
-            // the row loop has to fit the 18 KB instruction cache of an SM partition (profiles/r02_icache_probe.log)
-            if (single) {   // one predecessor: no argmax bookkeeping
+          // packed word of the column on my left (only its H matters)
+          int32_t wl = (lane == 0) ? hl0 * 32 : (left_ok ? row[kC * lane - 1] : NEGW);
+          if (single) {   // one predecessor: no argmax bookkeeping
 #pragma unroll
-              for (int c = 0; c < kC; ++c) {
-                cell_pred_single(acc[c], w[c], hl, (letter == rd[c]) ? s.m : s.n, s, tabs);
-                hl = unpack_h(w[c]);
-              }
-            } else {
-              const uint32_t k = e - nb;
+            for (int c = 0; c < kC; ++c) {
+              const int32_t sfv = __shfl_sync(0xffffffffu, lut.sf, w[c]);
+              const int32_t sov = __shfl_sync(0xffffffffu, lut.so, w[c]);
+              const int32_t smv = __shfl_sync(0xffffffffu, lut.sm, w[c]);
+              cell_pred_single(acc[c], w[c], unpack_h(wl), (letter == rd[c]) ? s.m : s.n, sfv, sov, smv);
+              wl = w[c];
+            }
+          } else {
+            const int32_t rk = 31 - static_cast<int32_t>(e - nb);
 #pragma unroll
-              for (int c = 0; c < kC; ++c) {
-                cell_pred_key(acc[c], k, w[c], hl, (letter == rd[c]) ? s.m : s.n, s, tabs);
-                hl = unpack_h(w[c]);
-              }
+            for (int c = 0; c < kC; ++c) {
+              const int32_t tfv = __shfl_sync(0xffffffffu, lut.tf, w[c]);
+              const int32_t tov = __shfl_sync(0xffffffffu, lut.to, w[c]);
+              const int32_t tvv = __shfl_sync(0xffffffffu, lut.tv, w[c]);
+              cell_pred_key(acc[c], rk, w[c], wl, tfv, tov, tvv);
+              wl = w[c];
             }
           }
+        }
+        if (!single) {
+#pragma unroll
+          for (int c = 0; c < kC; ++c) cell_key_add_sub(acc[c], (letter == rd[c]) ? s.m : s.n);
         }
 
         // ---- scan: horizontal gap states across the 256 columns of the warp ---------------------
@@ -408,8 +422,8 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
 #pragma unroll
           for (int c = 0; c < kC; ++c) {
             const int32_t A = single ? imax(acc[c].D, imax(acc[c].Fm, acc[c].Om))
-                                     : imax(key_value(acc[c].D), key_value(static_cast<int32_t>(acc[c].meta)));
-            if (c == kC - 1) { eloc7 = el; qloc7 = ql; a7 = imax(A, kNegBand); }
+                                     : imax(key_value_diag(acc[c].D), key_value(static_cast<int32_t>(acc[c].meta)));
+            if (c == kC - 1) { eloc7 = el; qloc7 = ql; a7 = A; }
             el = imax(A + s.g, el + s.e);
             ql = imax(A + s.q, ql + s.c);
           }
@@ -430,12 +444,11 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
         int32_t ve = el, vq = ql;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
+          // lanes below d get their own value back from the shuffle: own + (negative gap extension) never wins
           const int32_t oe = __shfl_up_sync(0xffffffffu, ve, d);
           const int32_t oq = __shfl_up_sync(0xffffffffu, vq, d);
-          if (lane >= d) {
-            ve = imax(ve, oe + kC * s.e * d);
-            vq = imax(vq, oq + kC * s.c * d);
-          }
+          ve = imax(ve, oe + kC * s.e * d);
+          vq = imax(vq, oq + kC * s.c * d);
         }
         int32_t ein = __shfl_up_sync(0xffffffffu, ve, 1);
         int32_t qin = __shfl_up_sync(0xffffffffu, vq, 1);
@@ -476,7 +489,6 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
         // ---- phase 2: H, traceback codes, packed row ---------------------------------------------
         if (t_active) {
           ++n_chunks;
-          int32_t hsel = INT32_MIN;
           uint8_t* crow = tk.codes + 8ull * row_coff;
           const uint32_t cidx = static_cast<uint32_t>(gc - clo);
           int32_t* rrow = ring + static_cast<size_t>(i % ring_rows) * 256 + kC * lane;
@@ -492,20 +504,16 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
               for (int c = 0; c < 4; ++c) {
                 int32_t H;
                 const uint32_t cd = cell_finish_single(acc[c], cy, s, H);
-                H = imax(H, kNegBand); cy.H = H; cy.A = imax(cy.A, kNegBand);   // pruned neighbours must not drift
                 wp[c] = pack_cell(H, acc[c].Fm, acc[c].Om);
                 if (c == 0) cw0 = cd; else if (c == 1) cw0 |= cd << 16; else if (c == 2) cw1 = cd; else cw1 |= cd << 16;
-                if (4 * h + c == c_end) hsel = H;
               }
             } else {
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 int32_t H, Fv, Ov;
                 const uint32_t cd = cell_finish_key(acc[c], cy, s, H, Fv, Ov);
-                H = imax(H, kNegBand); cy.H = H; cy.A = imax(cy.A, kNegBand);
                 wp[c] = pack_cell(H, Fv, Ov);
                 if (c == 0) cw0 = cd; else if (c == 1) cw0 |= cd << 16; else if (c == 2) cw1 = cd; else cw1 |= cd << 16;
-                if (4 * h + c == c_end) hsel = H;
               }
             }
             if (single) {   // low bytes only
@@ -519,9 +527,9 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[c] = acc[c + 4];
           }
-          if (owns_end && (rflags & kFlagSink) && hsel > best) {
-            best = hsel;
-            best_row = i;
+          if (owns_end && (rflags & kFlagSink)) {   // H of the last read column: my own packed cell, just stored
+            const int32_t hsel = unpack_h(rrow[c_end]);
+            if (hsel > best) { best = hsel; best_row = i; }
           }
         }
       }

@@ -297,7 +297,7 @@ poa_window_kernel(const WinParams P) {
           if (tid == 0) { tk.result[0] = 0; tk.result[1] = INT32_MIN; }
           compute_bands2<T>(x, tk, s, lb, have_lb, m.band, m.coff, static_cast<TbRow*>(m.tbrow), &s_need2);
           if (s_need2 > tk.codes_cap) { v2_overflow = true; break; }
-          dp2_align<T>(tk, s, P.tabs, P.ring_rows, smem_raw, m.band, m.coff, s_eval);
+          dp2_align<T>(tk, s, P.ring_rows, smem_raw, m.band, m.coff, s_eval);
           const int32_t found_row = tk.result[0], found = tk.result[1];
           if (!have_lb || (found_row > 0 && found >= lb)) break;
           if (tid == 0) s_retries += 1;

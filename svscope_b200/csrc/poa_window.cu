@@ -177,7 +177,6 @@ int launch_round(svs_poa_result* r, const std::vector<int>& groups, int tier_idx
   p.pairs_out = r->d_pairs;
   p.pair_cnt = r->d_pair_cnt;
   p.s = r->s;
-  p.tabs = make_single_tables(r->s);
   p.ring_rows = ctx->ring_rows;
   p.prune = ctx->prune;
   p.want_msa = r->want_msa ? 1 : 0;

@@ -52,7 +52,6 @@ struct WinParams {
   int32_t* pairs_out;         // debug: forward alignment pairs of every sequence, or nullptr
   int64_t* pair_cnt;          // debug: [members] pairs per sequence
   Scores s;
-  SingleTables tabs;
   int ring_rows;
   int prune;
   int want_msa;

@@ -70,7 +70,8 @@ static void emu_align(Emu* E, const uint8_t* read, uint32_t L) {
   std::vector<uint8_t> codes(n1_total * w1 + (R - n1_total) * w2 + 64);
   P[0] = pack_cell(0, kNeg, kNeg);
   for (uint32_t j = 1; j <= L; ++j) P[j] = pack_cell(row0_h(s, j), kNeg, kNeg);
-  const SingleTables tabs = make_single_tables(s);
+  PredLutEntry lut[32];
+  for (int low = 0; low < 32; ++low) lut[low] = pred_lut_entry(s, low);
   // depths for the pruning bounds
   std::vector<int32_t> dmin(R + 1, 0), dmax(R + 1, 0), smin(R + 1, 0), smax(R + 1, 0);
   std::vector<uint8_t> has_succ(R + 1, 0);
@@ -132,23 +133,28 @@ static void emu_align(Emu* E, const uint8_t* read, uint32_t L) {
         uint16_t cd;
         if (single) {  // the kernels' fast path
           const uint32_t p = G.preds[G.pred_off[i]];
-          cell_pred_single(a, P[p * W + j], unpack_h(P[p * W + j - 1]), sub, s, tabs);
+          const int32_t w = P[p * W + j];
+          const PredLutEntry& t = lut[w & 31];
+          cell_pred_single(a, w, unpack_h(P[p * W + j - 1]), sub, t.sf, t.so, t.sm);
           cd = static_cast<uint16_t>(cell_finish_single(a, cy, s, H));
         } else {
+          cell_key_init(a);
           for (uint32_t k = G.pred_off[i]; k < G.pred_off[i + 1]; ++k) {
             const uint32_t p = G.preds[k];
-            cell_pred_key(a, k - G.pred_off[i], P[p * W + j], unpack_h(P[p * W + j - 1]), sub, s, tabs);
+            const int32_t w = P[p * W + j];
+            const PredLutEntry& t = lut[w & 31];
+            cell_pred_key(a, 31 - static_cast<int32_t>(k - G.pred_off[i]), w, P[p * W + j - 1], t.tf, t.to, t.tv);
           }
+          cell_key_add_sub(a, sub);
           int32_t Fo, Oo;
           cd = cell_finish_key(a, cy, s, H, Fo, Oo);
           a.Fm = Fo; a.Om = Oo;
         }
-        if (E->prune > 0 && H < kNegBand) { H = kNegBand; cy.H = H; cy.A = std::max(cy.A, kNegBand); }
         const uint64_t n1 = G.single_before[i];
         uint8_t* crow = codes.data() + n1 * w1 + (static_cast<uint64_t>(i - 1) - n1) * w2;
         if (single) crow[j - 1] = static_cast<uint8_t>(cd);
         else reinterpret_cast<uint16_t*>(crow)[j - 1] = cd;
-        P[i * W + j] = pack_cell(H, std::max(a.Fm, kNegBand - 16), std::max(a.Om, kNegBand - 16));
+        P[i * W + j] = pack_cell(H, a.Fm, a.Om);
       }
       if ((G.flags[i] & kFlagSink) && cy.H > best && (E->prune == 0 || hi_col[i] >= static_cast<int32_t>(L))) {
         best = cy.H;
@@ -178,7 +184,8 @@ static bool emu_align_dyn(Emu* E, const uint8_t* read, uint32_t L, int32_t lb, i
   const uint32_t R = G.R;
   const uint64_t W = L + 1;
   const int C = 8;
-  const SingleTables tabs = make_single_tables(s);
+  PredLutEntry lut[32];
+  for (int low = 0; low < 32; ++low) lut[low] = pred_lut_entry(s, low);
   std::vector<int32_t> P((R + 1) * W, pack_cell(kNegBand, kNeg, kNeg));
   const uint32_t w1 = (L + 7 + 15) / 16 * 16, w2 = (L + 7 + 7) / 8 * 8 * 2;
   const uint64_t n1_total = G.single_before[R + 1];
@@ -242,18 +249,23 @@ static bool emu_align_dyn(Emu* E, const uint8_t* read, uint32_t L, int32_t lb, i
         int32_t H; uint16_t cd;
         if (single) {
           const uint32_t p = G.preds[G.pred_off[i]];
-          cell_pred_single(a, pw(p, j), unpack_h(pw(p, j - 1)), sub, s, tabs);
+          const int32_t w = pw(p, j);
+          const PredLutEntry& t = lut[w & 31];
+          cell_pred_single(a, w, unpack_h(pw(p, j - 1)), sub, t.sf, t.so, t.sm);
           cd = static_cast<uint16_t>(cell_finish_single(a, cy, s, H));
         } else {
+          cell_key_init(a);
           for (uint32_t k = G.pred_off[i]; k < G.pred_off[i + 1]; ++k) {
             const uint32_t p = G.preds[k];
-            cell_pred_key(a, k - G.pred_off[i], pw(p, j), unpack_h(pw(p, j - 1)), sub, s, tabs);
+            const int32_t w = pw(p, j);
+            const PredLutEntry& t = lut[w & 31];
+            cell_pred_key(a, 31 - static_cast<int32_t>(k - G.pred_off[i]), w, pw(p, j - 1), t.tf, t.to, t.tv);
           }
+          cell_key_add_sub(a, sub);
           int32_t Fo, Oo;
           cd = cell_finish_key(a, cy, s, H, Fo, Oo);
           a.Fm = Fo; a.Om = Oo;
         }
-        H = std::max(H, kNegBand); cy.H = H; cy.A = std::max(cy.A, kNegBand);
         const uint64_t n1 = G.single_before[i];
         uint8_t* crow = codes.data() + n1 * w1 + (static_cast<uint64_t>(i - 1) - n1) * w2;
         if (single) crow[j - 1] = static_cast<uint8_t>(cd);
