@@ -12,7 +12,8 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libsvscope_b200.so")
+# SVS_LIB: an instrumented build of the same library (scripts/dp_phase_profile.sh); never a different implementation
+LIB_PATH = os.environ.get("SVS_LIB") or os.path.join(_HERE, "_C", "libsvscope_b200.so")
 
 _lib = None
 _lock = threading.Lock()

@@ -24,14 +24,16 @@
 // tests/test_host_logic.py runs this arithmetic against the five-matrix oracle.
 //
 // Instead of keeping five score matrices for an equality-test traceback, every cell emits a
-// code holding exactly the decisions that traceback would take there (16 bits; rows with a
-// single predecessor keep only the low byte, their in-edge indices being 0):
-//   bits 0-1  move that defines H: 0 diagonal, 1 vertical, 2 horizontal
-//   bit  2    "extend" flag of a vertical / horizontal move (gap continues)
-//   bit  3    horizontal continuation: E[j]+e==E[j+1] || Q[j]+c==Q[j+1]
-//   bit  4    stop flag of the vertical-extension walk at this cell
-//   bits 5-9  in-edge index of the diagonal / vertical move
-//   bits 10-14 in-edge index of the vertical-extension walk (31 = none: go to the source row)
+// code holding exactly the decisions that traceback would take there (16 bits):
+//   bits 0-1   move that defines H: 0 diagonal, 1 vertical, 2 horizontal
+//   bit  2     "extend" flag of a vertical / horizontal move (gap continues)
+//   bit  3     horizontal continuation: E[j]+e==E[j+1] || Q[j]+c==Q[j+1]
+//   bits 5-9   31 - (in-edge index of the diagonal / vertical move)
+//   bit  10    stop flag of the vertical-extension walk at this cell
+//   bits 11-15 31 - (in-edge index of the vertical-extension walk); 0 = none: go to the source row
+// (the indices are stored complemented because that is how the max-keys of the fold carry them).
+// Rows with a single predecessor keep one byte per cell: bits 0-3 as above, bit 4 = stop flag,
+// their in-edge indices being 0 (code_of_single_byte widens it).
 #pragma once
 #include <cstdint>
 
@@ -60,9 +62,14 @@ SVS_HD int32_t imin(int32_t a, int32_t b) { return a < b ? a : b; }
 
 SVS_HD uint16_t make_code(uint32_t move, uint32_t ext, uint32_t lcnext, uint32_t upstop,
                           uint32_t k_move, uint32_t k_up) {
-  return static_cast<uint16_t>(move | (ext << 2) | (lcnext << 3) | (upstop << 4) | (k_move << 5) |
-                               (k_up << 10));
+  return static_cast<uint16_t>(move | (ext << 2) | (lcnext << 3) | ((31u - k_move) << 5) | (upstop << 10) |
+                               ((31u - k_up) << 11));
 }
+// the byte code of a single-predecessor row in the 16-bit layout (both in-edge indices 0)
+SVS_HD uint32_t code_of_single_byte(uint32_t b) { return (b & 15u) | ((b & 16u) << 6) | (31u << 5) | (31u << 11); }
+SVS_HD uint32_t code_kmove(uint32_t cd) { return 31u - ((cd >> 5) & 31u); }
+SVS_HD uint32_t code_stop(uint32_t cd) { return (cd >> 10) & 1u; }
+SVS_HD uint32_t code_kup(uint32_t cd) { return 31u - ((cd >> 11) & 31u); }
 
 // One word per cell carries all a successor row needs: H, and F and O as clamped distances
 // below H.  F matters to a successor only through max(H+g, F+e) and the equality tests
@@ -208,17 +215,16 @@ SVS_HD uint16_t cell_finish_key(const CellAcc& a, RowCarry& cy, const Scores& s,
   const uint32_t hx = (ee == H) || (cy.H + s.g != H && qe == H);
   const uint32_t move = is_d ? kMoveDiag : (is_v ? kMoveVert : kMoveHorz);
   const uint32_t ext = is_d ? 0u : (is_v ? static_cast<uint32_t>(kV & 1) : hx);
-  const uint32_t km = is_d ? 31u - (static_cast<uint32_t>(a.D) & 31u)
-                           : (is_v ? 31u - ((static_cast<uint32_t>(kV) >> 1) & 31u) : 0u);
+  // complemented in-edge index of the move, straight from the key (ignored for horizontal moves)
+  const uint32_t rmove = (is_d ? static_cast<uint32_t>(a.D) : (static_cast<uint32_t>(kV) >> 1)) & 31u;
   const uint32_t lcnext = (E + s.e >= A + s.g) || (Q + s.c >= A + s.q);
-  // vertical-extension walk: first in-edge attaining F or O (F wins ties)
-  const uint32_t iF = 31u - ((static_cast<uint32_t>(a.Fm) >> 1) & 31u);
-  const uint32_t iO = 31u - ((static_cast<uint32_t>(a.Om) >> 1) & 31u);
-  const uint32_t ku = iF <= iO ? iF : iO;
-  const uint32_t stop = iF <= iO ? static_cast<uint32_t>(a.Fm & 1) : static_cast<uint32_t>(a.Om & 1);
+  // vertical-extension walk: first in-edge attaining F or O (F wins ties).  The six low bits of a
+  // key are (31-k) << 1 | stop flag, exactly bits 10-15 of the code.
+  const uint32_t fF = static_cast<uint32_t>(a.Fm) & 63u, fO = static_cast<uint32_t>(a.Om) & 63u;
+  const uint32_t up = ((fF | 1u) >= fO) ? fF : fO;
   cy.A = A; cy.E = E; cy.Q = Q; cy.H = H;
   H_out = H; F_out = Fm; O_out = Om;
-  return make_code(move, ext, lcnext, stop, km, ku);
+  return static_cast<uint16_t>(move | (ext << 2) | (lcnext << 3) | (rmove << 5) | (up << 10));
 }
 
 // Traceback code of a source-row cell (0, j), j >= 1: always a horizontal move.
@@ -274,7 +280,7 @@ SVS_HD uint32_t tb_code_at(const TbView& v, const Scores& s, uint32_t ii, uint32
   const uint8_t* row = v.codes + n1 * v.w1 + (static_cast<uint64_t>(ii - 1) - n1) * v.w2;
   uint32_t col = jj - 1;
   if (v.band != nullptr) col -= (static_cast<uint32_t>(v.band[2 * ii] - 1) / v.cols) * v.cols;
-  if (v.pred_off[ii + 1] - v.pred_off[ii] == 1) return row[col];   // 1-byte code: in-edge indices are 0
+  if (v.pred_off[ii + 1] - v.pred_off[ii] == 1) return code_of_single_byte(row[col]);   // 1-byte code: in-edge indices are 0
   return reinterpret_cast<const uint16_t*>(row)[col];
 }
 
@@ -287,7 +293,7 @@ SVS_HD bool tb_step(const TbView& v, const Scores& s, uint32_t& i, uint32_t& j, 
     return k == kNoPred ? 0u : v.preds[v.pred_off[ii] + k];
   };
   const uint32_t cd = tb_code_at(v, s, i, j);
-  const uint32_t move = cd & 3, ext = (cd >> 2) & 1, km = (cd >> 5) & 31;
+  const uint32_t move = cd & 3, ext = (cd >> 2) & 1, km = code_kmove(cd);
   uint32_t pi, pj;
   if (move == kMoveDiag) { pi = pred_row(i, km); pj = j - 1; }
   else if (move == kMoveVert) { pi = pred_row(i, km); pj = j; }
@@ -309,7 +315,7 @@ SVS_HD bool tb_step(const TbView& v, const Scores& s, uint32_t& i, uint32_t& j, 
   } else if (move == kMoveVert && ext) {
     while (i != 0) {
       const uint32_t c2 = tb_code_at(v, s, i, j);
-      const uint32_t stop = (c2 >> 4) & 1, ku = (c2 >> 10) & 31;
+      const uint32_t stop = code_stop(c2), ku = code_kup(c2);
       const uint32_t up = pred_row(i, ku);
       if (n >= cap) return false;
       out_pairs[2 * n] = static_cast<int32_t>(v.node_id[i]);

@@ -20,6 +20,14 @@
 // Cell arithmetic, packed rows and code format: poa_cell.h (unchanged, proven against the
 // five-matrix oracle).
 
+// Profile builds (-DSVS_DP_PROFILE, scripts/dp_phase_profile.sh): lane 0 of every warp accumulates the cycles
+// between marks in the row loop; the totals of every alignment of CTA 0 are printed.  Off in the product.
+#ifdef SVS_DP_PROFILE
+#define DP_MARK(k) do { if (lane == 0) { const long long t_now = clock64(); prof_acc[k] += t_now - t_mark; t_mark = t_now; } } while (0)
+#else
+#define DP_MARK(k) do { } while (0)
+#endif
+
 constexpr int kCarryDepth = 64;
 constexpr int kStageCap = 160;   // predecessor entries staged per 32-row batch and warp
 
@@ -32,7 +40,8 @@ __host__ __device__ inline size_t dp2_smem_bytes(int threads, int ring_rows) {
   return static_cast<size_t>(threads) * 8 * 4 * (ring_rows + 2)   // packed-row rings + the source row + a scratch row
          + static_cast<size_t>(nw) * kCarryDepth * sizeof(Carry)
          + 128                                                  // prog[], fprog[]
-         + static_cast<size_t>(nw) * kStageCap * 12;            // staged predecessor entries
+         + static_cast<size_t>(nw) * kStageCap * 12             // staged predecessor entries
+         + static_cast<size_t>(nw) * 32 * 16;                   // row records of the running 32-row batch
 }
 
 struct __align__(16) TbRow {
@@ -204,6 +213,9 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
   // rows, not per row: the per-row hand-over between neighbouring warps is shared memory only
   volatile int* fprog = prog + 16;
   int32_t* stage = reinterpret_cast<int32_t*>(const_cast<int*>(prog) + 32) + warp * (kStageCap * 3);
+  // one 16-byte record per row of the running batch: chunk range, letter | flags | ring slot | need-left,
+  // predecessor entries, code offset; the row loop gets a row's metadata with one broadcast load
+  int4* mrec = reinterpret_cast<int4*>(reinterpret_cast<int32_t*>(const_cast<int*>(prog) + 32) + NW * (kStageCap * 3)) + warp * 32;
   int32_t* psrc = stage;                                        // source of the predecessor row
   uint32_t* pchk = reinterpret_cast<uint32_t*>(stage + kStageCap);   // its chunk range, lo | hi << 16
   int32_t* pbh = stage + 2 * kStageCap;                         // warp 0: H of the predecessor left of the strip
@@ -227,6 +239,12 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
   const int wlast = static_cast<int>(((tk.strip >> 3) - 1) >> 5);   // warp that owns the last chunk of a full strip
   long long t_wait_left = 0;   // cycles lane 0 spent polling its neighbours (per warp)
   const long long t_begin = clock64();
+#ifdef SVS_DP_PROFILE
+  __shared__ long long prof_all[16 * 10];
+  long long* prof_acc = prof_all + warp * 10;   // 0 batch staging, 1 early polls, 2 fold, 3 pre-scan, 4 wait for the left carry, 5 scan + publish, 6 finish, 7 skipped batches, 8 rows, 9 in-edges
+  if (lane == 0) for (int k = 0; k < 10; ++k) prof_acc[k] = 0;
+  long long t_mark = t_begin;
+#endif
   int next_check = 40;   // (absolute progress) next row at which I make sure not to lap the consumer of my carry ring
 
   for (uint32_t pass = 0; pass < tk.npass; ++pass) {
@@ -290,6 +308,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
         if (unfenced) { __threadfence_block(); unfenced = false; }
         if (lane == 31) { prog[warp] = pbase_prog + static_cast<int>(i0 + nrows - 1); fprog[warp] = pbase_prog + static_cast<int>(i0 + nrows - 1); }
         i0 += nrows;
+        DP_MARK(7);
         continue;
       }
       // left boundary of the strip (warp 0): column 0 in the first strip, else the state the
@@ -313,20 +332,29 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
       __syncwarp();
       const bool m_wait = dp2_stage_preds(tk, band, bin, m_inter, mi, m_poff, m_pend, pbase, m_clo, wc0, sc0, warp, pass, ring_rows,
                                           h_row0_left, psrc, pchk, pbh);
+      if (m_inter) {   // only rows with a cell in my columns are visited below
+        mrec[lane] = make_int4(static_cast<int>(static_cast<uint32_t>(m_clo) | (static_cast<uint32_t>(m_chi) << 16)),
+                               static_cast<int>(m_info | ((mi % static_cast<uint32_t>(ring_rows)) << 16) | (m_wait ? 1u << 24 : 0u)),
+                               static_cast<int>((m_poff - pbase) | ((m_pend - pbase) << 16)),
+                               static_cast<int>(m_coff));
+      }
       __syncwarp();
+      DP_MARK(0);
 
       for (uint32_t r = 0; r < nrows; ++r) {
         if (!((any >> r) & 1u)) continue;
         const uint32_t i = i0 + r;
-        const int32_t clo = __shfl_sync(0xffffffffu, m_clo, r);
-        const int32_t chi = __shfl_sync(0xffffffffu, m_chi, r);
-        const uint32_t info = __shfl_sync(0xffffffffu, m_info, r);
-        const uint32_t nb = __shfl_sync(0xffffffffu, m_poff, r) - pbase;
-        const uint32_t ne = __shfl_sync(0xffffffffu, m_pend, r) - pbase;
-        const uint32_t row_coff = __shfl_sync(0xffffffffu, m_coff, r);
-        const bool need_left = __shfl_sync(0xffffffffu, static_cast<int>(m_wait), r) != 0;
+        const int4 rec = mrec[r];
+        const int32_t clo = static_cast<int32_t>(static_cast<uint32_t>(rec.x) & 0xffffu);
+        const int32_t chi = static_cast<int32_t>(static_cast<uint32_t>(rec.x) >> 16);
+        const uint32_t info = static_cast<uint32_t>(rec.y);
+        const uint32_t nb = static_cast<uint32_t>(rec.z) & 0xffffu;
+        const uint32_t ne = static_cast<uint32_t>(rec.z) >> 16;
+        const uint32_t row_coff = static_cast<uint32_t>(rec.w);
+        const bool need_left = (info >> 24) != 0;
         const int32_t letter = static_cast<int32_t>(info & 0xffu);
-        const uint32_t rflags = info >> 8;
+        const uint32_t rflags = (info >> 8) & 0xffu;
+        const uint32_t rslot = (info >> 16) & 0xffu;   // i % ring_rows
         const bool single = (ne - nb == 1);
         const bool t_active = active && gc >= clo && gc <= chi;
         __syncwarp();   // the packed row my neighbours stored last is visible
@@ -349,6 +377,10 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
           __syncwarp();
           next_check = abs_i + 8;
         }
+        DP_MARK(1);
+#ifdef SVS_DP_PROFILE
+        if (lane == 0) { prof_acc[8] += 1; prof_acc[9] += ne - nb; }
+#endif
 
         // ---- phase 1: fold predecessor rows ---------------------------------------------------
         // Executed by every lane of the warp (the table look-ups are shuffles); lanes without a cell
@@ -415,6 +447,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
           for (int c = 0; c < kC; ++c) cell_key_add_sub(acc[c], (letter == rd[c]) ? s.m : s.n);
         }
 
+        DP_MARK(2);
         // ---- scan: horizontal gap states across the 256 columns of the warp ---------------------
         int32_t a7 = kNegBand;
         int32_t el = kNeg, ql = kNeg, eloc7 = kNeg, qloc7 = kNeg;
@@ -428,12 +461,14 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
             ql = imax(A + s.q, ql + s.c);
           }
         }
+        DP_MARK(3);
         if (warp > 0 && need_left) {   // the scan needs the left warp's state of THIS row
           if (lane == 0) { const long long t0 = clock64(); while (ld_prog(prog + warp - 1) < pbase_prog + static_cast<int>(i)) { } t_wait_left += clock64() - t0; }
           __syncwarp();
           asm volatile("" ::: "memory");
           if (clo < wc0) cin = carry_left[abs_i & (kCarryDepth - 1)];
         }
+        DP_MARK(4);
         int32_t ein0 = 0, qin0 = 0;
         if (lane == 0) {   // the state left of the warp enters through lane 0
           ein0 = imax(cin.A + s.g, cin.E + s.e);
@@ -486,13 +521,15 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
           prog[warp] = abs_i;
         }
 
+        DP_MARK(5);
         // ---- phase 2: H, traceback codes, packed row ---------------------------------------------
         if (t_active) {
           ++n_chunks;
           uint8_t* crow = tk.codes + 8ull * row_coff;
           const uint32_t cidx = static_cast<uint32_t>(gc - clo);
-          int32_t* rrow = ring + static_cast<size_t>(i % ring_rows) * 256 + kC * lane;
-          int32_t* xrow = (rflags & kFlagExport) ? tk.xrows + static_cast<uint64_t>(tk.xslot[i]) * tk.ldx + 3 + j0 : nullptr;
+          int32_t* rrow = ring + rslot * 256 + kC * lane;
+          int32_t* xrow = nullptr;
+          if (rflags & kFlagExport) xrow = tk.xrows + static_cast<uint64_t>(tk.xslot[i]) * tk.ldx + 3 + j0;
           // two halves of four cells through ONE copy of the cell code (instruction-cache footprint):
           // the second half's accumulators move into the first half's registers
 #pragma unroll 1
@@ -532,6 +569,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
             if (hsel > best) { best = hsel; best_row = i; }
           }
         }
+        DP_MARK(6);
       }
       // rows at the end of the batch that were skipped: tell the consumer
       if (i0 + nrows > R) {   // end of the pass: everything is stored
@@ -548,6 +586,14 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
   }
   const long long t_done = clock64();
   __syncthreads();
+#ifdef SVS_DP_PROFILE
+  if (blockIdx.x == 0 && lane == 0) {
+    printf("dpprof R %u L %u warp %d total %lld : stage %lld poll0 %lld fold %lld prescan %lld waitleft %lld scan %lld finish %lld skipped %lld | rows %lld inedges %lld\n",
+           tk.R, tk.L, warp, t_done - t_begin, prof_acc[0], prof_acc[1], prof_acc[2], prof_acc[3], prof_acc[4], prof_acc[5], prof_acc[6],
+           prof_acc[7], prof_acc[8], prof_acc[9]);
+  }
+  __syncthreads();
+#endif
   n_chunks = __reduce_add_sync(0xffffffffu, n_chunks);
   if (lane == 0 && eval_chunks != nullptr) {
     atomicAdd(eval_chunks, static_cast<unsigned long long>(n_chunks));
@@ -587,7 +633,7 @@ __device__ __forceinline__ uint32_t tb3_code_at(const TbCtx& v, const Scores& s,
   if (jj == 0) return v.col0code[ii];
   const uint8_t* row = v.codes + 8ull * R.coff;
   const uint32_t col = jj - 1 - (R.first_flags & ~7u);
-  if (R.first_flags & 1u) return row[col];
+  if (R.first_flags & 1u) return code_of_single_byte(row[col]);
   return reinterpret_cast<const uint16_t*>(row)[col];
 }
 
@@ -610,7 +656,7 @@ __device__ __forceinline__ void tb3_goto(const TbCtx& v, uint32_t& i, TbRow& cur
 __device__ bool tb3_step(const TbCtx& v, const Scores& s, uint32_t& i, uint32_t& j, TbRow& cur, TbRow& spec, int32_t& n,
                          int32_t* out_pairs, int32_t cap) {
   const uint32_t cd = tb3_code_at(v, s, cur, i, j);
-  const uint32_t move = cd & 3, ext = (cd >> 2) & 1, km = (cd >> 5) & 31;
+  const uint32_t move = cd & 3, ext = (cd >> 2) & 1, km = code_kmove(cd);
   uint32_t pi, pj;
   if (move == kMoveDiag) { pi = tb3_pred_row(v, cur, km); pj = j - 1; }
   else if (move == kMoveVert) { pi = tb3_pred_row(v, cur, km); pj = j; }
@@ -633,7 +679,7 @@ __device__ bool tb3_step(const TbCtx& v, const Scores& s, uint32_t& i, uint32_t&
   } else if (move == kMoveVert && ext) {
     while (i != 0) {
       const uint32_t c2 = tb3_code_at(v, s, cur, i, j);
-      const uint32_t stop = (c2 >> 4) & 1, ku = (c2 >> 10) & 31;
+      const uint32_t stop = code_stop(c2), ku = code_kup(c2);
       const uint32_t up = tb3_pred_row(v, cur, ku);
       if (n >= cap) return false;
       out_pairs[2 * n] = static_cast<int32_t>(cur.node_id);

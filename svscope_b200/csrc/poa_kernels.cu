@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
 
 #include "poa_cell.h"
 #include "poa_kernels.h"
