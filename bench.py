@@ -435,6 +435,7 @@ def main():
         "config": {"workload": WORKLOAD, "windows_per_step": len(windows), "windows_per_gpu": len(windows),
                    "configs1_batch": CONFIGS1_BATCH, "reads_per_window": 60, "edit_distance_matrix": ed,
                    "step_batch_note": ("the configs[1] batch" if len(windows) == CONFIGS1_BATCH else
+                                       f"--windows {len(windows_all)}: a smaller batch of the same distribution" if calib is None or len(windows) == len(windows_all) else
                                        f"first {len(windows)} windows of the {len(windows_all)}-window batch per step, so that "
                                        f"{args.steps} steps fit {args.budget_s:.0f} s (the full batch takes "
                                        f"{calib['full_batch_step_s']:.1f} s per step: calibration)"),
@@ -458,9 +459,14 @@ def main():
                 "pruning_retries_per_step": st.get("poa_prune_retries", 0.0),
                 "failed_windows_per_step": st.get("poa_failed_windows", 0.0),
                 "phase_share": {k: v / cyc_tot for k, v in cyc.items()},
-                "dp_warps": {"working": (st.get("poa_wcyc_loop", 0.0) - st.get("poa_wcyc_wait_left", 0.0)) / wl,
-                             "waiting_for_neighbour": st.get("poa_wcyc_wait_left", 0.0) / wl,
-                             "waiting_at_end": st.get("poa_wcyc_wait_end", 0.0) / wl},
+                "dp_warps": {"working": (st.get("poa_wcyc_loop", 0.0) - st.get("poa_wcyc_wait_left", 0.0)
+                                         - st.get("poa_wcyc_wait_right", 0.0)) / wl,
+                             "waiting_for_handover": st.get("poa_wcyc_wait_left", 0.0) / wl,
+                             "waiting_at_row_start": st.get("poa_wcyc_wait_right", 0.0) / wl,
+                             "waiting_at_end": st.get("poa_wcyc_wait_end", 0.0) / wl,
+                             "note": "lane-0 clocks of every warp; waiting_at_row_start = left neighbour not yet one row behind or "
+                                     "right neighbour more than 32 rows behind (the strips ramp up and down one after the other: "
+                                     "profiles/r02_dp_phase_profile_summary.txt)"},
                 "host_ms_per_step": 0.0},
         "edit_distance": {"cells_per_step": st.get("ed_cells", 0.0), "kernel_ms_per_step": st.get("ed_ms", 0.0)},
         "em_output_windows": sum(r[-1].endswith("EMOutput") for r in out.records),

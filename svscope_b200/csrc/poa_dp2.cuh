@@ -237,7 +237,8 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
   int next_fence = 0;
   bool unfenced = false;   // rows processed since my last fence
   const int wlast = static_cast<int>(((tk.strip >> 3) - 1) >> 5);   // warp that owns the last chunk of a full strip
-  long long t_wait_left = 0;   // cycles lane 0 spent polling its neighbours (per warp)
+  long long t_wait_left = 0;   // cycles lane 0 spent polling for the state its left neighbour hands over (per warp)
+  long long t_wait_pipe = 0;   // ... and polling at the start of a row: left neighbour one row behind, right neighbour 32 rows behind
   const long long t_begin = clock64();
 #ifdef SVS_DP_PROFILE
   __shared__ long long prof_all[16 * 10];
@@ -367,13 +368,13 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
           cin.E = __shfl_sync(0xffffffffu, m_bE, r);
           cin.Q = __shfl_sync(0xffffffffu, m_bQ, r);
         } else if (need_left) {   // predecessor rows left of my span: the left warp must have done row i - 1
-          if (lane == 0) { while (ld_prog(prog + warp - 1) < pbase_prog + static_cast<int>(i) - 1) { } }
+          if (lane == 0) { const long long t0 = clock64(); while (ld_prog(prog + warp - 1) < pbase_prog + static_cast<int>(i) - 1) { } t_wait_pipe += clock64() - t0; }
           __syncwarp();
           asm volatile("" ::: "memory");
         }
         const int abs_i = pbase_prog + static_cast<int>(i);   // carry-ring slots are indexed by absolute progress
         if (NW > 1 && warp + 1 < NW && abs_i >= next_check) {
-          if (lane == 0) { while (ld_prog(prog + warp + 1) < abs_i - 32) { } }
+          if (lane == 0) { const long long t0 = clock64(); while (ld_prog(prog + warp + 1) < abs_i - 32) { } t_wait_pipe += clock64() - t0; }
           __syncwarp();
           next_check = abs_i + 8;
         }
@@ -599,7 +600,7 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
     atomicAdd(eval_chunks, static_cast<unsigned long long>(n_chunks));
     atomicAdd(eval_chunks + 1, static_cast<unsigned long long>(t_done - t_begin));        // busy + polling, per warp
     atomicAdd(eval_chunks + 2, static_cast<unsigned long long>(t_wait_left));
-    atomicAdd(eval_chunks + 3, 0ull);
+    atomicAdd(eval_chunks + 3, static_cast<unsigned long long>(t_wait_pipe));
     atomicAdd(eval_chunks + 4, static_cast<unsigned long long>(clock64() - t_done));        // waiting for the slowest warp at the end
   }
 }
