@@ -228,6 +228,9 @@ def _bic(lik: np.ndarray, K: int, nf: int, zero_params: int = 0) -> float:
     return 2 * lik.sum() - n_theta * np.log(len(lik))     # :218
 
 
+EM_MAX_READS = 1024   # rows of one window the mixture kernel takes (csrc/em.cu)
+
+
 def _resume_fit(ctx, X, K, labels, first, want_theta):
     """Finish one (window, K) fit whose M-step hit the re-draw condition (pi*N < 1 or NaN,
     ReadsCluster.py:179-187).  theta is drawn on the host from numpy's global RNG exactly as
@@ -448,6 +451,12 @@ def localgraph_batch(windows, ctx: Optional[Context] = None, reads: Optional[Rea
         em_idx, Xs, sims, zps = [], [], [], []
         for k, (enc, (keep, nf, zp, ident)) in enumerate(zip(encs, feats)):
             n = enc.shape[0] - 1
+            if n > EM_MAX_READS and nf >= 10:
+                # the mixture kernel holds one window's responsibilities in shared memory (svs_em_batch: 1..1024
+                # rows): such a window fails alone with a flagged record, the batch goes on
+                records[part[k]][9] = flags[part[k]] + "|MixtureLimit%d" % n
+                n_failed += 1
+                continue
             if n != 0 and nf >= 10:                                            # DecisionMaker.py:137
                 X = np.ascontiguousarray(enc[1:][:, keep])
                 sim = ident.astype(np.float64) / nf

@@ -541,3 +541,23 @@ def test_batch_host_orchestration_equals_oracle_with_device_stand_ins(oracle, mo
                 assert [str(x) for x in want] == [str(x) for x in g]
                 n_em += str(g[-1]).endswith("EMOutput")
     assert n_em >= 10
+
+
+def test_window_beyond_the_mixture_limit_fails_alone(oracle, monkeypatch):
+    """A window with more rows than the mixture kernel takes gets a flagged record; its neighbours in
+    the batch still equal the oracle (one outlier must not fail the batch)."""
+    import warnings
+    _device_stand_ins(oracle, monkeypatch)
+    monkeypatch.setattr(batch, "EM_MAX_READS", 12)
+    small = synth.make_sv_window(5, 200, "DEL", 40, 5, 5, 3, 0.03)
+    big = synth.make_sv_window(6, 200, "INS", 40, 9, 9, 4, 0.03)          # 18 reads > 12
+    other = synth.make_sv_window(7, 240, "DEL", 50, 6, 5, 3, 0.03)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = batch.localgraph_batch([small, big, other], ctx=object())
+        got = out.records
+        for w, g in ((small, got[0]), (other, got[2])):
+            want = oracle.decision(w[4], w[0], w[1], w[2], w[3])
+            assert [str(x) for x in want] == [str(x) for x in g]
+    assert got[1][9].endswith("|MixtureLimit18") and got[1][3] == "-" and got[1][5] == 0
+    assert out.stats["poa_failed_windows"] == 1
