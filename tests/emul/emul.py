@@ -51,6 +51,8 @@ def lib():
         L.emu_retries.argtypes = [ctypes.c_void_p]
         L.emu_kept_fraction.restype = ctypes.c_double
         L.emu_kept_fraction.argtypes = [ctypes.c_void_p]
+        L.emu_cell_selfcheck.restype = ctypes.c_int64
+        L.emu_cell_selfcheck.argtypes = [ctypes.c_uint32, ctypes.c_int64, ctypes.c_void_p]
         L.dgraph_emul_check.restype = ctypes.c_int
         L.dgraph_emul_check.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
@@ -68,6 +70,13 @@ def dgraph_check(seqs, ring_rows=4, n_threads=128, serial_rank=False):
     rc = lib().dgraph_emul_check(b"".join(enc), off.ctypes.data, len(enc), ring_rows, n_threads,
                                  1 if serial_rank else 0, msg, 512)
     return "" if rc == 0 else (msg.value.decode() or "mismatch")
+
+
+def cell_selfcheck(seed=1, n_random=2000):
+    """(mismatches, comparisons) of the shared cell header's self-check (poa_emul.cpp emu_cell_selfcheck)."""
+    n = ctypes.c_int64()
+    bad = lib().emu_cell_selfcheck(seed, n_random, ctypes.byref(n))
+    return int(bad), int(n.value)
 
 
 class EmuSession:

@@ -361,4 +361,76 @@ void emu_msa(void* h, char* out) {
   size_t off = 0;
   for (auto& r : m) { std::memcpy(out + off, r.data(), r.size()); off += r.size(); }
 }
+
+// Self-check of the shared cell header: the predecessor table against the definitions it tabulates, the
+// key fold against a direct "first in-edge attaining the maximum", and the code fields against their decoders.
+// Returns the number of mismatches (0 = fine); *checked = number of comparisons made.
+int64_t emu_cell_selfcheck(uint32_t seed, int64_t n_random, int64_t* checked) {
+  int64_t bad = 0, cnt = 0;
+  auto rnd = [&seed]() { seed = seed * 1664525u + 1013904223u; return seed >> 8; };
+  for (int g = -10; g <= -2; ++g) for (int e = g + 1; e <= std::min(g + 2, -1); ++e)
+    for (int c = e + 1; c <= -1; ++c) for (int q = std::max(-10, c - 6); q < g; ++q) {
+      const Scores s{5, -4, g, e, q, c};
+      PredLutEntry lut[32];
+      for (int low = 0; low < 32; ++low) {
+        lut[low] = pred_lut_entry(s, low);
+        const int dF = (low >> 3) & 3, dO = low & 7;
+        const int Fc = std::max(g, e - dF), Oc = std::max(q, c - dO), V = std::max(Fc, Oc);
+        const int xv = ((e - dF == V) || (g != V && c - dO == V)) ? 1 : 0;
+        bad += lut[low].sf != Fc || lut[low].so != Oc || lut[low].sm != (xv | ((g >= e - dF) ? 2 : 0));
+        bad += lut[low].tf != Fc * 64 + ((g >= e - dF) ? 1 : 0) - 2 * low;
+        bad += lut[low].to != Oc * 64 + ((q >= c - dO) ? 1 : 0) - 2 * low;
+        bad += lut[low].tv != V * 64 + xv - 2 * low;
+        cnt += 4;
+      }
+      for (int64_t it = 0; it < n_random; ++it) {   // random in-edge sets through the key fold
+        const int d = 1 + static_cast<int>(rnd() % 6);
+        const int32_t sub = (rnd() & 1) ? s.m : s.n;
+        int32_t w[6], wl[6];
+        for (int k = 0; k < d; ++k) {
+          const int32_t base = static_cast<int32_t>(rnd() % 64) - 32;     // close values: ties are frequent
+          w[k] = pack_cell(base, base - static_cast<int32_t>(rnd() % 5), base - static_cast<int32_t>(rnd() % 9));
+          wl[k] = pack_cell(static_cast<int32_t>(rnd() % 16) - 8, kNeg, kNeg);
+        }
+        CellAcc a; cell_key_init(a);
+        for (int k = 0; k < d; ++k) {
+          const PredLutEntry& t = lut[w[k] & 31];
+          cell_pred_key(a, 31 - k, w[k], wl[k], t.tf, t.to, t.tv);
+        }
+        cell_key_add_sub(a, sub);
+        // direct evaluation
+        int32_t Fm = INT32_MIN, Om = INT32_MIN, Dm = INT32_MIN, Vm = INT32_MIN; int iF = 0, iO = 0, iD = 0, iV = 0;
+        int fF = 0, fO = 0, fV = 0;
+        for (int k = 0; k < d; ++k) {
+          int32_t H, F, O; unpack_cell(w[k], H, F, O);
+          const int32_t G = H + g, Fe = F + e, Oq = H + q, Oe = O + c;
+          const int32_t Fc = std::max(G, Fe), Oc = std::max(Oq, Oe), V = std::max(Fc, Oc), D = unpack_h(wl[k]) + sub;
+          if (Fc > Fm) { Fm = Fc; iF = k; fF = G >= Fe; }
+          if (Oc > Om) { Om = Oc; iO = k; fO = Oq >= Oe; }
+          if (D > Dm) { Dm = D; iD = k; }
+          if (V > Vm) { Vm = V; iV = k; fV = (Fe == V) || (G != V && Oe == V); }
+        }
+        bad += (a.Fm >> 6) != Fm || 31 - ((a.Fm >> 1) & 31) != iF || (a.Fm & 1) != fF;
+        bad += (a.Om >> 6) != Om || 31 - ((a.Om >> 1) & 31) != iO || (a.Om & 1) != fO;
+        bad += (a.D >> 5) != Dm || 31 - (a.D & 31) != iD;
+        const int32_t kV = static_cast<int32_t>(a.meta);
+        bad += (kV >> 6) != Vm || 31 - ((kV >> 1) & 31) != iV || (kV & 1) != fV;
+        cnt += 4;
+      }
+    }
+  for (uint32_t move = 0; move < 3; ++move) for (uint32_t bits = 0; bits < 8; ++bits)
+    for (uint32_t km = 0; km < 32; ++km) for (uint32_t ku = 0; ku < 32; ++ku) {
+      const uint32_t cd = make_code(move, bits & 1, (bits >> 1) & 1, bits >> 2, km, ku);
+      bad += (cd & 3) != move || ((cd >> 2) & 1) != (bits & 1) || ((cd >> 3) & 1) != ((bits >> 1) & 1) ||
+             code_stop(cd) != (bits >> 2) || code_kmove(cd) != km || code_kup(cd) != ku;
+      ++cnt;
+    }
+  for (uint32_t b = 0; b < 32; ++b) {   // byte codes of single-predecessor rows
+    const uint32_t cd = code_of_single_byte(b);
+    bad += (cd & 15) != (b & 15) || code_stop(cd) != ((b >> 4) & 1) || code_kmove(cd) != 0 || code_kup(cd) != 0;
+    ++cnt;
+  }
+  if (checked) *checked = cnt;
+  return bad;
+}
 }

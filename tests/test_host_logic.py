@@ -561,3 +561,12 @@ def test_window_beyond_the_mixture_limit_fails_alone(oracle, monkeypatch):
             assert [str(x) for x in want] == [str(x) for x in g]
     assert got[1][9].endswith("|MixtureLimit18") and got[1][3] == "-" and got[1][5] == 0
     assert out.stats["poa_failed_windows"] == 1
+
+
+def test_cell_header_table_keys_and_codes_selfcheck():
+    """poa_cell.h: the 32-entry predecessor table equals the definitions it tabulates for every supported
+    gap-parameter set, the shuffle-table key fold equals a direct 'first in-edge attaining the maximum' on
+    random in-edge sets with frequent ties, and every code field survives make_code -> decoder."""
+    from tests.emul.emul import cell_selfcheck
+    bad, n = cell_selfcheck(seed=7, n_random=300)
+    assert n > 100000 and bad == 0
