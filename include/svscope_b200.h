@@ -38,11 +38,11 @@ int svs_create(int device, svs_ctx** out);
 void svs_destroy(svs_ctx* ctx);
 const char* svs_last_error(const svs_ctx* ctx);
 const char* svs_version(void);
-/* Options (all optional): "poa_threads" CTA size of the window kernel (128|256|512; default
- * 128), "poa_cols" read columns per thread (4 with 512 threads | 8 | 16 with 256 threads; default
- * 8), "ring_rows" packed rows kept in shared memory (default 10), "prune" exact score-bound
- * pruning (default 1), "arena_mb" device scratch arena in MiB (0 = 85 % of free memory).
- * Resident windows per SM: 4 for 128x8, 2 for 256x8, 1 for 256x16 / 512x8 / 512x4. */
+/* Options (all optional): "poa_threads" CTA size of the window kernel (128|256|384|512; default
+ * 384: twelve warps on one alignment, one resident window per SM), "poa_cols" read columns per
+ * thread (8), "ring_rows" packed rows kept in shared memory per warp (default 8; limited by the
+ * 227 KB of shared memory of an SM), "prune" exact score-bound pruning (default 1), "arena_mb"
+ * device scratch arena in MiB (0 = 85 % of free memory), "dp_kernel" (2: the warp-pipelined DP). */
 int svs_set_option(svs_ctx* ctx, const char* key, int64_t value);
 int64_t svs_get_option(const svs_ctx* ctx, const char* key);
 
