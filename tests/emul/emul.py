@@ -13,12 +13,12 @@ _lib = None
 
 def build(force=False):
     srcs = [os.path.join(HERE, "poa_emul.cpp"), os.path.join(HERE, "dgraph_emul.cpp"),
-            os.path.join(HERE, "poa_graph.cpp")]
-    deps = srcs + [os.path.join(HERE, "poa_graph.h")] + [os.path.join(ROOT, "svscope_b200", "csrc", h)
-                                                          for h in ("poa_cell.h", "poa_dgraph.h", "poa_task.h")]
+            os.path.join(HERE, "poa_graph.cpp"), os.path.join(HERE, "dp2_threads.cpp"), os.path.join(HERE, "cuda_shim.cpp")]
+    deps = srcs + [os.path.join(HERE, "poa_graph.h"), os.path.join(HERE, "cuda_shim.h")] + [
+        os.path.join(ROOT, "svscope_b200", "csrc", h) for h in ("poa_cell.h", "poa_dgraph.h", "poa_task.h", "poa_dp2.cuh")]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w"] + srcs + ["-o", LIB], check=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-pthread"] + srcs + ["-o", LIB], check=True)
     return LIB
 
 
@@ -41,6 +41,9 @@ def lib():
         L.emu_msa_dims.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.emu_msa.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.emu_set_prune.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.emu_set_warp.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.emu_warp_retries.restype = ctypes.c_int
+        L.emu_warp_retries.argtypes = [ctypes.c_void_p]
         L.emu_set_dyn.argtypes = [ctypes.c_void_p, ctypes.c_double]
         L.emu_set_dyn_ext.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.emu_static_fraction.restype = ctypes.c_double
@@ -80,8 +83,11 @@ def cell_selfcheck(seed=1, n_random=2000):
 
 
 class EmuSession:
-    def __init__(self, ring_rows=4, prune=0, dyn=None, dyn_ext=None):
+    def __init__(self, ring_rows=4, prune=0, dyn=None, dyn_ext=None, warp_threads=0, warp_prune=0):
         self.h = lib().emu_new(ring_rows)
+        if warp_threads:
+            # the product's warp-pipelined DP source on that many OS threads (dp2_threads.cpp)
+            lib().emu_set_warp(self.h, int(warp_threads), int(warp_prune))
         if dyn_ext is not None:
             lib().emu_set_dyn_ext(self.h, int(dyn_ext))
         if prune:
@@ -91,6 +97,9 @@ class EmuSession:
 
     def retries(self):
         return lib().emu_retries(self.h)
+
+    def warp_retries(self):
+        return lib().emu_warp_retries(self.h)
 
     def kept_fraction(self):
         return lib().emu_kept_fraction(self.h)

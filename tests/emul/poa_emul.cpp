@@ -29,7 +29,18 @@ struct Emu {
   uint32_t ring_rows = 4;
   std::vector<int32_t> last;  // forward pairs
   RankedGraph rg;
+  // > 0: run the product's warp-pipelined DP source (poa_dp2.cuh) on that many OS threads (dp2_threads.cpp)
+  int warp_threads = 0;
+  int warp_prune = 0;
+  int warp_retries = 0;
+  int32_t last_score = 0;
+  uint32_t last_len = 0;
 };
+
+namespace svs {
+int dp2_threads_align(const RankedGraph& G, const PoaScoring& sc, const uint8_t* read, uint32_t L, int threads, int ring_rows,
+                      bool prune, int32_t lb_guess, std::vector<int32_t>* rev_pairs, int32_t* score, int* retries);
+}
 
 static bool emu_align_dyn(Emu* E, const uint8_t* read, uint32_t L, int32_t lb, int32_t* score_out);
 
@@ -37,6 +48,26 @@ static void emu_align(Emu* E, const uint8_t* read, uint32_t L) {
   E->last.clear();
   if (E->graph.empty() || L == 0) return;
   E->graph.export_ranked(E->sc, E->ring_rows, &E->rg);
+  if (E->warp_threads > 0) {
+    // poa_kernels.cu: pruning from a guessed lower bound (score per base of the previous read minus a margin);
+    // the size thresholds are lowered here so that small test inputs run the banded path too
+    const bool prune = E->warp_prune != 0 && L >= 64 && E->rg.R >= 64;
+    const double spb = E->last_len ? static_cast<double>(E->last_score) / E->last_len : 4.0;
+    const int32_t lb_guess = static_cast<int32_t>((spb - 0.10) * static_cast<double>(L)) - 40;
+    std::vector<int32_t> rev;
+    int32_t score = 0;
+    int retries = 0;
+    const int rc = dp2_threads_align(E->rg, E->sc, read, L, E->warp_threads, static_cast<int>(E->ring_rows), prune, lb_guess, &rev,
+                                     &score, &retries);
+    if (rc != 0) { E->last.assign(2, -999); return; }   // shows up as a mismatch in the test
+    E->warp_retries += retries;
+    E->last_score = score; E->last_len = L;
+    for (int64_t k = static_cast<int64_t>(rev.size() / 2) - 1; k >= 0; --k) {
+      E->last.push_back(rev[2 * k]);
+      E->last.push_back(rev[2 * k + 1]);
+    }
+    return;
+  }
   if (E->dyn) {
     int32_t lb = static_cast<int32_t>(E->lb_ratio * L), score = 0;
     const int ext0 = E->dyn_ext;
@@ -308,6 +339,8 @@ void* emu_new(int ring_rows) {
   e->ring_rows = ring_rows;
   return e;
 }
+void emu_set_warp(void* h, int threads, int prune) { static_cast<Emu*>(h)->warp_threads = threads; static_cast<Emu*>(h)->warp_prune = prune; }
+int emu_warp_retries(void* h) { return static_cast<Emu*>(h)->warp_retries; }
 void emu_set_prune(void* h, int half_width) { static_cast<Emu*>(h)->prune = half_width; }
 void emu_set_dyn_ext(void* h, int chunks) { static_cast<Emu*>(h)->dyn_ext = chunks; }
 double emu_static_fraction(void* h) { Emu* e = static_cast<Emu*>(h); return e->all_cells > 0 ? e->static_cells / e->all_cells : 1.0; }
