@@ -108,6 +108,8 @@ int dp2_threads_align(const RankedGraph& G, const PoaScoring& sc, const uint8_t*
   const Scores s{sc.m, sc.n, sc.g, sc.e, sc.q, sc.c};
   if (threads == 128) return run<128>(G, s, read, L, ring_rows, prune, lb_guess, rev_pairs, score, retries);
   if (threads == 256) return run<256>(G, s, read, L, ring_rows, prune, lb_guess, rev_pairs, score, retries);
+  if (threads == 384) return run<384>(G, s, read, L, ring_rows, prune, lb_guess, rev_pairs, score, retries);
+  if (threads == 512) return run<512>(G, s, read, L, ring_rows, prune, lb_guess, rev_pairs, score, retries);
   return -3;
 }
 
