@@ -14,9 +14,11 @@ N>1 (torchrun, one rank per GPU): every rank gets its own batch of the same dist
 `e2e`     the same step through the public batch call with host buffers (read upload and all
           result copies inside the timed region).
 Batch size of a step: the configs[1] batch (1000 windows) unless K steps of it would not fit
-`--budget-s` seconds (the driver allows 870 s per run); then every step takes the first n
-windows of the batch, n chosen from one untimed full-size step, and the JSON line says so
-(`config.windows_per_step`).  Warm-up steps run on a 64-window slice (context, arena, kernels).
+`--budget-s` seconds / the whole process would not fit `--total-s` (the driver allows 870 s
+per run); then every step takes the first n windows of the batch, n chosen from one untimed
+full-size step and one untimed step of n windows, and the JSON line says so
+(`run.windows_per_step`).  `config` holds the workload only and is the same dict in both arms;
+what is specific to this implementation and run is under `run`.  Warm-up steps run on a 64-window slice (context, arena, kernels).
 `--impl reference`  times the CPU path (oracle port of the reference: pyspoa is not
           installable offline) on a bounded sample with all host cores, once.
 """
@@ -34,6 +36,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+_T_IMPORT = time.time()
 sys.path.insert(0, ROOT)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before any CUDA context (see svscope_b200/__init__.py)
 if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL would print its version on stdout, next to the JSON line
@@ -153,6 +156,38 @@ def sum_over_ranks(x):
     return _reduce(x, "SUM")
 
 
+def process_age_s():
+    """Seconds since this process started (interpreter start-up and the first `import torch` included)."""
+    try:
+        import psutil
+        return max(0.0, time.time() - psutil.Process().create_time())
+    except Exception:
+        return time.time() - _T_IMPORT
+
+
+def usable_cores(gb_per_process=10.0):
+    """Host threads the CPU arm uses: the cores this process may run on, capped so that one oracle process per
+    core (five int32 matrices of one alignment: up to ~8 GB for a configs[1] window) fits the free memory."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        avail_kb = next(int(l.split()[1]) for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
+        n = min(n, max(1, int(avail_kb / 1048576.0 / gb_per_process)))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def workload_config(n_windows, edit_distance, world):
+    """`config` of BOTH arms (ours and --impl reference print the same dict): the workload only."""
+    return {"workload": WORKLOAD, "windows_per_gpu": n_windows, "configs1_batch": CONFIGS1_BATCH,
+            "reads_per_window": 60, "edit_distance_matrix": bool(edit_distance),
+            "parallelism": f"dp{world}: every rank its own batch of windows, no collective on the data path",
+            "l2": "GPU arm: inputs larger than L2 (reads + traceback codes >> 126 MB per step); CPU arm: not applicable"}
+
+
 def make_batch(n_windows, rank):
     from svscope_b200 import synth
     return [synth.make_c2_window(rank * n_windows + i) for i in range(n_windows)]
@@ -206,7 +241,7 @@ def _cpu_worker(args):
 def cpu_rates(windows, budget_s=20.0, cores=None):
     """Scalar-port rates on `cores` windows spread evenly over the cost-sorted batch, one process each."""
     import multiprocessing as mp
-    cores = min(cores or os.cpu_count() or 1, len(windows))
+    cores = min(cores or usable_cores(), len(windows))
     costs = np.array([model_cells(w) for w in windows])
     order = np.argsort(costs)
     picks = [int(order[int((k + 0.5) * len(order) / cores)]) for k in range(cores)]
@@ -250,8 +285,11 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--windows", type=int, default=CONFIGS1_BATCH, help="windows per rank and step (configs[1]: 1000)")
-    ap.add_argument("--budget-s", type=float, default=520.0,
+    ap.add_argument("--budget-s", type=float, default=480.0,
                     help="seconds the K timed steps may take; the per-step batch shrinks to fit (0: never shrink)")
+    ap.add_argument("--total-s", type=float, default=740.0,
+                    help="seconds the whole process should take (the driver allows 870 s per run); the timed budget "
+                         "shrinks if start-up, warm-up and calibration took long (0: ignore)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-edit-distance", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -296,23 +334,46 @@ def main():
     slice_reads.close()
 
     # ---- per-step batch: the configs[1] batch, or its first n windows if K steps would not fit ------
+    # The driver allows 870 s for the whole process.  The timed steps get what `--total-s` leaves after the
+    # time already spent (process start, imports, batch generation, warm-up, calibration) and the work that
+    # follows them (the host-buffer step, the CPU sample at N=1), at most `--budget-s`.
     n_step = len(windows_all)
     calib = None
+    budget_s = args.budget_s
     if args.budget_s > 0 and args.steps > 1:
         reads_all = upload_windows(ctx, windows_all)
         barrier_sync()
         t_c = time.perf_counter()
-        out_c = run(windows_all, reads_all)
+        run(windows_all, reads_all)
         torch.cuda.synchronize()
         t_full = max_over_ranks(time.perf_counter() - t_c)
         calib = {"full_batch_windows": len(windows_all), "full_batch_step_s": t_full,
                  "full_batch_windows_per_s_per_gpu": len(windows_all) / t_full}
-        if t_full * args.steps > args.budget_s:
-            n_step = int(len(windows_all) * args.budget_s / (t_full * args.steps) / 1.04)
+        if args.total_s > 0:
+            after = 15.0 + (args.cpu_budget + 8.0 if (world == 1 and not args.no_cpu_baseline) else 0.0)
+            avail = args.total_s - process_age_s() - after - 0.5 * t_full      # 0.5 t_full: the second calibration step
+            share = args.steps / (args.steps + (0.0 if args.no_e2e else 1.1))    # the host-buffer step follows
+            budget_s = min_over_ranks(max(30.0, min(budget_s, avail * share)))
+        if t_full * args.steps > budget_s:
+            n_step = int(len(windows_all) * budget_s / (t_full * args.steps) / 1.04)
             n_step = int(min_over_ranks(float(max(64, min(len(windows_all), n_step)))))
         if n_step < len(windows_all):
+            # a step of n windows is not n/1000 of the full step (fewer windows per SM, longer tail): one
+            # untimed step at the chosen size, then shrink once more if it says so
             reads_all.close()
             reads_all = None
+            sub = windows_all[:n_step]
+            reads_sub = upload_windows(ctx, sub)
+            barrier_sync()
+            t_c = time.perf_counter()
+            run(sub, reads_sub)
+            torch.cuda.synchronize()
+            t_sub = max_over_ranks(time.perf_counter() - t_c)
+            reads_sub.close()
+            calib.update(second_calibration_windows=n_step, second_calibration_step_s=t_sub)
+            if t_sub * args.steps > 1.02 * budget_s:
+                n_step = int(min_over_ranks(float(max(64, int(n_step * budget_s / (t_sub * args.steps))))))
+        calib["timed_budget_s"] = budget_s
     else:
         reads_all = upload_windows(ctx, windows_all)
     windows = windows_all[:n_step]
@@ -320,6 +381,7 @@ def main():
     read_bytes = reads.nbytes
 
     # ---- timed region ------------------------------------------------------------------------------
+    t_before_timed = process_age_s()
     sampler = ClockSampler(local)
     barrier_sync()
     if rank == 0:
@@ -432,18 +494,18 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_max / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32 (POA DP, edit distance u32 bit-vectors), f64 (mixture model)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "windows_per_step": len(windows), "windows_per_gpu": len(windows),
-                   "configs1_batch": CONFIGS1_BATCH, "reads_per_window": 60, "edit_distance_matrix": ed,
-                   "step_batch_note": ("the configs[1] batch" if len(windows) == CONFIGS1_BATCH else
-                                       f"--windows {len(windows_all)}: a smaller batch of the same distribution" if calib is None or len(windows) == len(windows_all) else
-                                       f"first {len(windows)} windows of the {len(windows_all)}-window batch per step, so that "
-                                       f"{args.steps} steps fit {args.budget_s:.0f} s (the full batch takes "
-                                       f"{calib['full_batch_step_s']:.1f} s per step: calibration)"),
-                   "warmup_note": f"{max(args.warmup, 1)} warm-up steps on the 64 cheapest windows of the batch ({t_w:.1f} s)",
-                   "l2": "inputs larger than L2 (reads + traceback codes >> 126 MB per step)",
-                   "parallelism": f"windows sharded over {world} GPU(s), no collective; host work per rank: one Python process",
-                   "poa_threads": ctx.get_option("poa_threads"), "ring_rows": ctx.get_option("ring_rows"),
-                   "sub_batches": int(out.stats.get("sub_batches", 1))},
+        "config": workload_config(len(windows_all), ed, world),
+        "run": {"windows_per_step": len(windows),
+                "step_batch_note": ("the configs[1] batch" if len(windows) == CONFIGS1_BATCH else
+                                    f"--windows {len(windows_all)}: a smaller batch of the same distribution" if calib is None or len(windows) == len(windows_all) else
+                                    f"first {len(windows)} windows of the {len(windows_all)}-window batch per step, so that "
+                                    f"{args.steps} steps fit {budget_s:.0f} s (the full batch takes "
+                                    f"{calib['full_batch_step_s']:.1f} s per step: calibration)"),
+                "warmup_note": f"{max(args.warmup, 1)} warm-up steps on the 64 cheapest windows of the batch ({t_w:.1f} s)",
+                "host_work_per_rank": "one Python process (+ one thread driving the edit-distance kernels)",
+                "poa_threads": ctx.get_option("poa_threads"), "ring_rows": ctx.get_option("ring_rows"),
+                "sub_batches": int(out.stats.get("sub_batches", 1)),
+                "seconds_before_timed_region": round(t_before_timed, 1)},
         "calibration": calib,
         "e2e": e2e,
         "gpu_launches": int(agg.get("poa_dp_launches", 0) + agg.get("aux_launches", 0)),
@@ -514,10 +576,9 @@ def main_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["wall_s"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64 (CPU)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "windows_per_gpu": args.windows, "reads_per_window": 60,
-                       "edit_distance_matrix": ed,
-                       "sample_note": "one bounded sample, timed once (the driver's steps/warmup are echoed, not repeated); "
-                                      "cells per window from the growth model of bench.model_cells x (1 + consensus share)"},
+            "config": workload_config(args.windows, ed, env_int("WORLD_SIZE", 1)),
+            "run": {"sample_note": "one bounded sample, timed once (the driver's steps/warmup are echoed, not repeated); "
+                                   "cells per window from the growth model of bench.model_cells x (1 + consensus share)"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "value_without_edit_distance",
                                                 "value_with_edit_distance", "poa_gcups_per_core", "ed_gcups_per_core")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

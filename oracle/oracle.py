@@ -73,6 +73,10 @@ def lib():
         L.spo_consensus.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
         L.spo_msa_dims.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.spo_msa.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.spo_set_blocked.argtypes = [ctypes.c_void_p, ctypes.c_int64]
+        for fn in ("spo_blocked_kept_rows", "spo_blocked_recomputed"):
+            getattr(L, fn).restype = ctypes.c_int64
+            getattr(L, fn).argtypes = [ctypes.c_void_p]
         L.lev_dp.restype = ctypes.c_int64
         L.lev_dp.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_char_p, ctypes.c_int64]
         L.lev_myers.restype = ctypes.c_int64
@@ -91,11 +95,22 @@ def lib():
 class PoaSession:
     """Step-wise access to the restated spoa graph (alignment pairs, rank order, edges)."""
 
-    def __init__(self, algorithm: int = 1, m=5, n=-4, g=-8, e=-6, q=-10, c=-4):
+    def __init__(self, algorithm: int = 1, m=5, n=-4, g=-8, e=-6, q=-10, c=-4, block_rows: int = 0):
+        """``block_rows``: 0 = flat five-matrix engine; > 0 = row-checkpoint engine with that many
+        rows per block; -1 = row-checkpoint engine with ~2 GB blocks (bounded memory: windows whose
+        full matrices do not fit, e.g. BASELINE configs[2] at full size).  Same recurrences, same
+        traceback code (spoa_oracle.cpp: trace_back)."""
         self._h = lib().spo_new(algorithm, m, n, g, e, q, c)
         if not self._h:
             raise ValueError("oracle supports the convex gap mode only (g<e, g>q, e<c)")
         self.cells = 0
+        if block_rows:
+            lib().spo_set_blocked(self._h, int(block_rows))
+
+    @property
+    def blocked_stats(self) -> dict:
+        return dict(kept_rows=int(lib().spo_blocked_kept_rows(self._h)),
+                    recomputed_blocks=int(lib().spo_blocked_recomputed(self._h)))
 
     def close(self):
         if self._h:
@@ -166,11 +181,11 @@ class PoaSession:
 
 
 def poa(sequences: Sequence[str], algorithm: int = 0, genmsa: bool = True, m=5, n=-4, g=-8,
-        e=-6, q=-10, c=-4, min_coverage=None) -> Tuple[str, List[str]]:
+        e=-6, q=-10, c=-4, min_coverage=None, block_rows: int = 0) -> Tuple[str, List[str]]:
     """Signature of ``spoa.poa`` (pyspoa 0.2.1).  ``min_coverage`` is not restated."""
     if min_coverage is not None:
         raise NotImplementedError("min_coverage is not used by the reference")
-    s = PoaSession(algorithm, m, n, g, e, q, c)
+    s = PoaSession(algorithm, m, n, g, e, q, c, block_rows=block_rows)
     try:
         for seq in sequences:
             s.add(seq)

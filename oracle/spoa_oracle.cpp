@@ -23,6 +23,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -306,6 +307,114 @@ struct Graph {
   }
 };
 
+// Matrix access of the flat five-matrix engine.
+struct FlatMatrices {
+  const int32_t *Hm, *Fm, *Em, *Om, *Qm;
+  uint64_t W;
+  void ensure(uint64_t) {}
+  int32_t H(uint64_t i, uint64_t j) const { return Hm[i * W + j]; }
+  int32_t F(uint64_t i, uint64_t j) const { return Fm[i * W + j]; }
+  int32_t E(uint64_t i, uint64_t j) const { return Em[i * W + j]; }
+  int32_t O(uint64_t i, uint64_t j) const { return Om[i * W + j]; }
+  int32_t Q(uint64_t i, uint64_t j) const { return Qm[i * W + j]; }
+};
+
+// Traceback by ordered equality tests on the filled matrices: the ONE statement of the tie-break
+// precedence (diagonal over the in-edges in stored order, then vertical, then horizontal; gap
+// extension walks).  M gives the matrix values; M.ensure(i) is called before row i becomes the
+// row the walk stands on (a no-op for flat matrices; the row-checkpoint engine recomputes the
+// block of rows that holds i).
+template <class Mat>
+Alignment trace_back(Mat& M, AlnType type, int32_t e, int32_t g, int32_t q, int32_t c,
+                     const std::vector<int32_t>& profile, uint64_t W, const std::vector<Node*>& rn,
+                     const std::vector<uint32_t>& rank_of, uint32_t best_i, uint32_t best_j) {
+  Alignment aln;
+  uint64_t i = best_i, j = best_j;
+  auto going = [&]() {
+    M.ensure(i);
+    if (type == kSW) return M.H(i, j) != 0;
+    if (type == kNW) return !(i == 0 && j == 0);
+    return !(i == 0 || j == 0);
+  };
+  uint64_t prev_i = 0, prev_j = 0;
+  while (going()) {
+    const int32_t Hij = M.H(i, j);
+    bool found = false, ext_left = false, ext_up = false;
+    if (i != 0 && j != 0) {
+      Node* node = rn[i - 1];
+      const int32_t s = profile[node->code * W + j];
+      uint64_t pi = node->in.empty() ? 0 : rank_of[node->in[0]->tail->id] + 1;
+      if (Hij == M.H(pi, j - 1) + s) {
+        prev_i = pi; prev_j = j - 1; found = true;
+      } else {
+        for (size_t p = 1; p < node->in.size(); ++p) {
+          pi = rank_of[node->in[p]->tail->id] + 1;
+          if (Hij == M.H(pi, j - 1) + s) {
+            prev_i = pi; prev_j = j - 1; found = true;
+            break;
+          }
+        }
+      }
+    }
+    if (!found && i != 0) {
+      Node* node = rn[i - 1];
+      auto vertical = [&](uint64_t pi) {
+        return (ext_up |= (Hij == M.F(pi, j) + e)) || Hij == M.H(pi, j) + g ||
+               (ext_up |= (Hij == M.O(pi, j) + c)) || Hij == M.H(pi, j) + q;
+      };
+      uint64_t pi = node->in.empty() ? 0 : rank_of[node->in[0]->tail->id] + 1;
+      if (vertical(pi)) {
+        prev_i = pi; prev_j = j; found = true;
+      } else {
+        for (size_t p = 1; p < node->in.size(); ++p) {
+          pi = rank_of[node->in[p]->tail->id] + 1;
+          if (vertical(pi)) {
+            prev_i = pi; prev_j = j; found = true;
+            break;
+          }
+        }
+      }
+    }
+    if (!found && j != 0) {
+      if ((ext_left |= (Hij == M.E(i, j - 1) + e)) || Hij == M.H(i, j - 1) + g ||
+          (ext_left |= (Hij == M.Q(i, j - 1) + c)) || Hij == M.H(i, j - 1) + q) {
+        prev_i = i; prev_j = j - 1; found = true;
+      }
+    }
+    aln.emplace_back(i == prev_i ? -1 : static_cast<int32_t>(rn[i - 1]->id),
+                     j == prev_j ? -1 : static_cast<int32_t>(j - 1));
+    i = prev_i;
+    j = prev_j;
+    if (ext_left) {
+      M.ensure(i);
+      while (true) {
+        aln.emplace_back(-1, static_cast<int32_t>(j - 1));
+        --j;
+        if (M.E(i, j) + e != M.E(i, j + 1) && M.Q(i, j) + c != M.Q(i, j + 1)) break;
+      }
+    } else if (ext_up) {
+      while (true) {
+        M.ensure(i);
+        bool stop = true;
+        prev_i = 0;
+        for (Edge* ed : rn[i - 1]->in) {
+          uint64_t pi = rank_of[ed->tail->id] + 1;
+          if ((stop = (M.F(i, j) == M.H(pi, j) + g)) || M.F(i, j) == M.F(pi, j) + e ||
+              (stop = (M.O(i, j) == M.H(pi, j) + q)) || M.O(i, j) == M.O(pi, j) + c) {
+            prev_i = pi;
+            break;
+          }
+        }
+        aln.emplace_back(static_cast<int32_t>(rn[i - 1]->id), -1);
+        i = prev_i;
+        if (stop || i == 0) break;
+      }
+    }
+  }
+  std::reverse(aln.begin(), aln.end());
+  return aln;
+}
+
 struct Engine {
   AlnType type;
   GapMode mode;
@@ -466,98 +575,209 @@ struct Engine {
     if (best_i == 0 && best_j == 0) return Alignment();
     last_score = best;
 
-    // traceback by ordered equality tests
-    Alignment aln;
-    uint64_t i = best_i, j = best_j;
-    auto going = [&]() {
-      if (type == kSW) return H[i * W + j] != 0;
-      if (type == kNW) return !(i == 0 && j == 0);
-      return !(i == 0 || j == 0);
-    };
-    uint64_t prev_i = 0, prev_j = 0;
-    while (going()) {
-      const int32_t Hij = H[i * W + j];
-      bool found = false, ext_left = false, ext_up = false;
-      if (i != 0 && j != 0) {
-        Node* node = rn[i - 1];
-        const int32_t s = profile[node->code * W + j];
-        uint64_t pi = node->in.empty() ? 0 : rank_of[node->in[0]->tail->id] + 1;
-        if (Hij == H[pi * W + j - 1] + s) {
-          prev_i = pi; prev_j = j - 1; found = true;
+    // traceback by ordered equality tests (shared with the row-checkpoint engine below)
+    FlatMatrices mats{H, F, E, O, Q, W};
+    Alignment aln = trace_back(mats, type, e, g, q, c, profile, W, rn, rank_of, best_i, best_j);
+    return aln;
+  }
+};
+
+// Row-checkpoint engine: the same recurrences and the same traceback (trace_back above), with
+// bounded memory.  Rows are filled in blocks of `block_rows` ranks; a block keeps its five matrices
+// only while it is the current block.  A row with a successor in a LATER block is kept (H, F, O)
+// for the rest of the alignment, so every block can be recomputed from kept rows alone; the
+// traceback recomputes the block that holds the row it stands on (each block at most once, since
+// the walk only moves to lower ranks).  Used for windows whose five full matrices do not fit
+// in memory (BASELINE configs[2] at full size: ~150k x 20k cells); tests/test_oracle_blocked.py
+// checks it against the flat engine, alignment by alignment, with blocks of a few rows.
+struct BlockedEngine {
+  int32_t m, n, g, e, q, c;
+  int64_t block_rows_opt = -1;   // -1: sized for ~2 GB per block
+  std::vector<uint32_t> rank_of;
+  std::vector<int32_t> profile;
+  std::vector<int32_t> row0[5];        // H F E O Q of the virtual source row
+  std::vector<int32_t> H0, F0, O0;     // column 0 of every row
+  std::vector<int32_t> blk[5];         // H F E O Q of the current block
+  uint64_t blk_first = 0, blk_count = 0, W = 0, B = 0;
+  std::unordered_map<uint64_t, std::unique_ptr<int32_t[]>> kept;   // row -> H, F, O (3W)
+  const Graph* gr = nullptr;
+  int64_t last_cells = 0, kept_rows = 0, recomputed_blocks = 0;
+  int32_t last_score = 0;
+  int32_t best = 0;
+  uint32_t best_i = 0, best_j = 0;
+
+  BlockedEngine(int m_, int n_, int g_, int e_, int q_, int c_) : m(m_), n(n_), g(g_), e(e_), q(q_), c(c_) {}
+
+  struct RowPtr { const int32_t *H, *F, *O; };
+  RowPtr pred_row(uint64_t pi) const {
+    if (pi == 0) return {row0[0].data(), row0[1].data(), row0[3].data()};
+    if (pi >= blk_first && pi < blk_first + blk_count) {
+      const uint64_t o = (pi - blk_first) * W;
+      return {blk[0].data() + o, blk[1].data() + o, blk[3].data() + o};
+    }
+    auto it = kept.find(pi);
+    if (it == kept.end()) throw std::logic_error("row-checkpoint engine: predecessor row neither in the block nor kept");
+    return {it->second.get(), it->second.get() + W, it->second.get() + 2 * W};
+  }
+
+  // fills rows [first, first+count); `forward` = first visit (keeps rows, tracks the end cell)
+  void compute_block(uint64_t first, uint64_t count, bool forward) {
+    blk_first = first;
+    blk_count = 0;          // rows become visible to pred_row one by one
+    const auto& rn = gr->rank_to_node;
+    for (uint64_t i = first; i < first + count; ++i) {
+      Node* node = rn[i - 1];
+      const int32_t* __restrict prof = &profile[node->code * W];
+      const uint64_t o = (i - first) * W;
+      int32_t* __restrict Hr = blk[0].data() + o;
+      int32_t* __restrict Fr = blk[1].data() + o;
+      int32_t* __restrict Er = blk[2].data() + o;
+      int32_t* __restrict Or = blk[3].data() + o;
+      int32_t* __restrict Qr = blk[4].data() + o;
+      Hr[0] = H0[i]; Fr[0] = F0[i]; Or[0] = O0[i]; Er[0] = kNegInf; Qr[0] = kNegInf;
+      const size_t np = node->in.size();
+      for (size_t p = 0; p < std::max<size_t>(np, 1); ++p) {
+        const uint64_t pi = np == 0 ? 0 : rank_of[node->in[p]->tail->id] + 1;
+        const RowPtr pr = pred_row(pi);
+        if (p == 0) {
+          for (uint64_t j = 1; j < W; ++j) {
+            Fr[j] = std::max(pr.H[j] + g, pr.F[j] + e);
+            Or[j] = std::max(pr.H[j] + q, pr.O[j] + c);
+            Hr[j] = pr.H[j - 1] + prof[j];
+          }
         } else {
-          for (size_t p = 1; p < node->in.size(); ++p) {
-            pi = rank_of[node->in[p]->tail->id] + 1;
-            if (Hij == H[pi * W + j - 1] + s) {
-              prev_i = pi; prev_j = j - 1; found = true;
-              break;
-            }
+          for (uint64_t j = 1; j < W; ++j) {
+            Fr[j] = std::max(Fr[j], std::max(pr.H[j] + g, pr.F[j] + e));
+            Or[j] = std::max(Or[j], std::max(pr.H[j] + q, pr.O[j] + c));
+            Hr[j] = std::max(Hr[j], pr.H[j - 1] + prof[j]);
           }
         }
       }
-      if (!found && i != 0) {
-        Node* node = rn[i - 1];
-        auto vertical = [&](uint64_t pi) {
-          return (ext_up |= (Hij == F[pi * W + j] + e)) || Hij == H[pi * W + j] + g ||
-                 (ext_up |= (Hij == O[pi * W + j] + c)) || Hij == H[pi * W + j] + q;
-        };
-        uint64_t pi = node->in.empty() ? 0 : rank_of[node->in[0]->tail->id] + 1;
-        if (vertical(pi)) {
-          prev_i = pi; prev_j = j; found = true;
-        } else {
-          for (size_t p = 1; p < node->in.size(); ++p) {
-            pi = rank_of[node->in[p]->tail->id] + 1;
-            if (vertical(pi)) {
-              prev_i = pi; prev_j = j; found = true;
-              break;
-            }
-          }
-        }
+      int32_t hl = Hr[0], el = Er[0], ql = Qr[0];
+      for (uint64_t j = 1; j < W; ++j) {
+        el = std::max(hl + g, el + e);
+        ql = std::max(hl + q, ql + c);
+        hl = std::max(Hr[j], std::max(std::max(Fr[j], el), std::max(Or[j], ql)));
+        Er[j] = el; Qr[j] = ql; Hr[j] = hl;
       }
-      if (!found && j != 0) {
-        if ((ext_left |= (Hij == E[i * W + j - 1] + e)) || Hij == H[i * W + j - 1] + g ||
-            (ext_left |= (Hij == Q[i * W + j - 1] + c)) || Hij == H[i * W + j - 1] + q) {
-          prev_i = i; prev_j = j - 1; found = true;
-        }
-      }
-      aln.emplace_back(i == prev_i ? -1 : static_cast<int32_t>(rn[i - 1]->id),
-                       j == prev_j ? -1 : static_cast<int32_t>(j - 1));
-      i = prev_i;
-      j = prev_j;
-      if (ext_left) {
-        while (true) {
-          aln.emplace_back(-1, static_cast<int32_t>(j - 1));
-          --j;
-          if (E[i * W + j] + e != E[i * W + j + 1] && Q[i * W + j] + c != Q[i * W + j + 1]) break;
-        }
-      } else if (ext_up) {
-        while (true) {
-          bool stop = true;
-          prev_i = 0;
-          for (Edge* ed : rn[i - 1]->in) {
-            uint64_t pi = rank_of[ed->tail->id] + 1;
-            if ((stop = (F[i * W + j] == H[pi * W + j] + g)) || F[i * W + j] == F[pi * W + j] + e ||
-                (stop = (O[i * W + j] == H[pi * W + j] + q)) || O[i * W + j] == O[pi * W + j] + c) {
-              prev_i = pi;
-              break;
-            }
-          }
-          aln.emplace_back(static_cast<int32_t>(rn[i - 1]->id), -1);
-          i = prev_i;
-          if (stop || i == 0) break;
-        }
+      blk_count = i - first + 1;
+      if (forward && node->out.empty() && W > 1 && best < Hr[W - 1]) {
+        best = Hr[W - 1]; best_i = static_cast<uint32_t>(i); best_j = static_cast<uint32_t>(W - 1);
       }
     }
-    std::reverse(aln.begin(), aln.end());
+    if (!forward) { ++recomputed_blocks; return; }
+    for (uint64_t i = first; i < first + count; ++i) {
+      bool later = false;
+      for (Edge* ed : rn[i - 1]->out) later |= rank_of[ed->head->id] + 1 >= first + count;
+      if (!later) continue;
+      std::unique_ptr<int32_t[]> row(new int32_t[3 * W]);
+      const uint64_t o = (i - first) * W;
+      std::memcpy(row.get(), blk[0].data() + o, W * 4);
+      std::memcpy(row.get() + W, blk[1].data() + o, W * 4);
+      std::memcpy(row.get() + 2 * W, blk[3].data() + o, W * 4);
+      kept.emplace(i, std::move(row));
+      ++kept_rows;
+      if (static_cast<uint64_t>(kept_rows) * 3 * W * 4 > (40ull << 30)) throw std::runtime_error("row-checkpoint engine: kept rows exceed 40 GB");
+    }
+  }
+
+  // trace_back's view
+  void ensure(uint64_t i) {
+    if (i == 0 || (i >= blk_first && i < blk_first + blk_count)) return;
+    const uint64_t first = 1 + (i - 1) / B * B;
+    compute_block(first, std::min<uint64_t>(B, gr->nodes.size() + 1 - first), false);
+  }
+  const int32_t* own(int k, uint64_t i) const {
+    if (i == 0) return row0[k].data();
+    if (i >= blk_first && i < blk_first + blk_count) return blk[k].data() + (i - blk_first) * W;
+    return nullptr;
+  }
+  int32_t H(uint64_t i, uint64_t j) const { const int32_t* r = own(0, i); return r ? r[j] : pred_row(i).H[j]; }
+  int32_t F(uint64_t i, uint64_t j) const { const int32_t* r = own(1, i); return r ? r[j] : pred_row(i).F[j]; }
+  int32_t O(uint64_t i, uint64_t j) const { const int32_t* r = own(3, i); return r ? r[j] : pred_row(i).O[j]; }
+  int32_t E(uint64_t i, uint64_t j) const {
+    const int32_t* r = own(2, i);
+    if (!r) throw std::logic_error("row-checkpoint engine: E of a row outside the current block");
+    return r[j];
+  }
+  int32_t Q(uint64_t i, uint64_t j) const {
+    const int32_t* r = own(4, i);
+    if (!r) throw std::logic_error("row-checkpoint engine: Q of a row outside the current block");
+    return r[j];
+  }
+
+  Alignment align(const char* seq, uint32_t len, const Graph& graph) {
+    last_cells = 0; kept_rows = 0; recomputed_blocks = 0;
+    if (graph.nodes.empty() || len == 0) return Alignment();
+    if (!(g < e && !(g <= q || e >= c))) throw std::invalid_argument("oracle restates the convex (two-piece) gap mode only");
+    {
+      int64_t worst = static_cast<int64_t>(std::min(std::min(g, q), std::min(e, c))) *
+                      (static_cast<int64_t>(len) + static_cast<int64_t>(graph.nodes.size()) + 2);
+      if (worst < kNegInf) throw std::invalid_argument("possible score overflow");
+    }
+    gr = &graph;
+    W = static_cast<uint64_t>(len) + 1;
+    const uint64_t Hh = graph.nodes.size() + 1;
+    const auto& rn = graph.rank_to_node;
+    last_cells = static_cast<int64_t>(W * Hh);
+    B = block_rows_opt > 0 ? static_cast<uint64_t>(block_rows_opt) : std::max<uint64_t>(64, (2ull << 30) / (20 * W));
+    B = std::min(B, Hh);
+    for (auto& v : blk) if (v.size() < B * W) { v.clear(); v.shrink_to_fit(); v.resize(B * W); }
+    kept.clear();
+    blk_first = 0; blk_count = 0;
+    if (profile.size() < graph.num_codes * W) profile.resize(graph.num_codes * W);
+    if (rank_of.size() < graph.nodes.size()) rank_of.resize(graph.nodes.size());
+    for (uint32_t k = 0; k < graph.num_codes; ++k) {
+      char ch = static_cast<char>(graph.decoder[k]);
+      profile[k * W] = 0;
+      for (uint32_t j = 0; j < len; ++j) profile[k * W + j + 1] = (ch == seq[j]) ? m : n;
+    }
+    for (uint32_t r = 0; r < rn.size(); ++r) rank_of[rn[r]->id] = r;
+    // boundary conditions of the global alignment (Engine::init, kNW)
+    for (auto& v : row0) v.assign(W, 0);
+    for (uint64_t j = 1; j < W; ++j) {
+      row0[3][j] = kNegInf; row0[4][j] = q + static_cast<int32_t>(j - 1) * c;
+      row0[1][j] = kNegInf; row0[2][j] = g + static_cast<int32_t>(j - 1) * e;
+      row0[0][j] = std::max(row0[4][j], row0[2][j]);
+    }
+    H0.assign(Hh, 0); F0.assign(Hh, 0); O0.assign(Hh, 0);
+    for (uint64_t i = 1; i < Hh; ++i) {
+      const auto& in = rn[i - 1]->in;
+      int32_t po = in.empty() ? q - c : kNegInf, pf = in.empty() ? g - e : kNegInf;
+      for (Edge* ed : in) {
+        po = std::max(po, O0[rank_of[ed->tail->id] + 1]);
+        pf = std::max(pf, F0[rank_of[ed->tail->id] + 1]);
+      }
+      O0[i] = po + c; F0[i] = pf + e; H0[i] = std::max(O0[i], F0[i]);
+    }
+    best = kNegInf; best_i = 0; best_j = 0;
+    for (uint64_t first = 1; first < Hh; first += B) compute_block(first, std::min<uint64_t>(B, Hh - first), true);
+    if (best_i == 0 && best_j == 0) return Alignment();
+    last_score = best;
+    Alignment aln = trace_back(*this, kNW, e, g, q, c, profile, W, rn, rank_of, best_i, best_j);
+    kept.clear();
     return aln;
   }
 };
 
 struct Session {
   Engine engine;
+  BlockedEngine blocked;
+  bool use_blocked = false;
   Graph graph;
   Alignment last;
   std::string err;
-  Session(int t, int m, int n, int g, int e, int q, int c) : engine(t, m, n, g, e, q, c) {}
+  Session(int t, int m, int n, int g, int e, int q, int c) : engine(t, m, n, g, e, q, c), blocked(m, n, g, e, q, c) {}
+  Alignment align(const char* seq, uint32_t len) {
+    if (use_blocked) {
+      if (engine.type != kNW) throw std::invalid_argument("row-checkpoint engine: global alignment only");
+      Alignment a = blocked.align(seq, len, graph);
+      engine.last_cells = blocked.last_cells;
+      engine.last_score = blocked.last_score;
+      return a;
+    }
+    return engine.align(seq, len, graph);
+  }
 };
 
 }  // namespace
@@ -579,7 +799,7 @@ void spo_free(void* h) { delete static_cast<Session*>(h); }
 int64_t spo_add(void* h, const char* seq, int64_t len) {
   Session* s = static_cast<Session*>(h);
   try {
-    s->last = s->engine.align(seq, static_cast<uint32_t>(len), s->graph);
+    s->last = s->align(seq, static_cast<uint32_t>(len));
     s->graph.add_alignment(s->last, seq, static_cast<uint32_t>(len));
     return static_cast<int64_t>(s->last.size());
   } catch (const std::exception& ex) {
@@ -592,7 +812,7 @@ int64_t spo_add(void* h, const char* seq, int64_t len) {
 int64_t spo_align_only(void* h, const char* seq, int64_t len) {
   Session* s = static_cast<Session*>(h);
   try {
-    s->last = s->engine.align(seq, static_cast<uint32_t>(len), s->graph);
+    s->last = s->align(seq, static_cast<uint32_t>(len));
     return static_cast<int64_t>(s->last.size());
   } catch (const std::exception& ex) {
     s->err = ex.what();
@@ -609,6 +829,16 @@ int64_t spo_last_alignment(void* h, int32_t* node_ids, int32_t* positions, int64
   }
   return static_cast<int64_t>(s->last.size());
 }
+
+// Row-checkpoint engine for the following alignments: block_rows > 0 rows per block, -1 sized for
+// ~2 GB per block, 0 back to the flat five-matrix engine.
+void spo_set_blocked(void* h, int64_t block_rows) {
+  Session* s = static_cast<Session*>(h);
+  s->use_blocked = block_rows != 0;
+  s->blocked.block_rows_opt = block_rows;
+}
+int64_t spo_blocked_kept_rows(void* h) { return static_cast<Session*>(h)->blocked.kept_rows; }
+int64_t spo_blocked_recomputed(void* h) { return static_cast<Session*>(h)->blocked.recomputed_blocks; }
 
 int64_t spo_last_cells(void* h) { return static_cast<Session*>(h)->engine.last_cells; }
 int32_t spo_last_score(void* h) { return static_cast<Session*>(h)->engine.last_score; }

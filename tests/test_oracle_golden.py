@@ -130,3 +130,63 @@ def test_levenshtein_agrees_with_an_independent_engine(oracle):
         n += 1
         assert sum(m.fuzzy_counts) == oracle.levenshtein(a, b) == oracle.levenshtein(a, b, bitparallel=True)
     assert n > 250
+
+
+def _flat_equals_blocked(oracle, seqs, block_rows):
+    a, b = oracle.PoaSession(1), oracle.PoaSession(1, block_rows=block_rows)
+    try:
+        for x in seqs:
+            pa, pb = a.add(x), b.add(x)
+            assert np.array_equal(pa, pb), (block_rows, len(x))
+            if len(pa):
+                assert a.score == b.score
+        assert a.msa() == b.msa() and a.consensus() == b.consensus()
+        return b.blocked_stats
+    finally:
+        a.close()
+        b.close()
+
+
+def test_row_checkpoint_engine_equals_flat_engine(oracle, golden_dir):
+    """The bounded-memory engine (blocks of rows, kept rows, blocks recomputed by the traceback) gives the flat
+    five-matrix engine's alignments read after read: frozen cases, windows with deletions / insertions /
+    tandem repeats, empty reads, blocks of 1..64 rows (so that blocks, kept rows and recomputation are all hit)."""
+    from svscope_b200 import synth
+    cases = json.load(open(os.path.join(golden_dir, "poa_cases.json")))["cases"]
+    recomputed = kept = 0
+    for cs in cases:
+        for B in (1, 3, 16):
+            st = _flat_equals_blocked(oracle, cs["seqs"], B)
+            recomputed += st["recomputed_blocks"]
+            kept += st["kept_rows"]
+    rng = np.random.default_rng(11)
+    for seed in range(12):
+        w = synth.make_small_window(100 + seed, body_len=int(rng.integers(30, 260)), sv_len=int(rng.integers(5, 90)),
+                                    n_tumor=6, n_normal=6, n_carriers=3, sv_type="INS" if seed % 2 else "DEL")
+        seqs = list(w[0])
+        if seed % 4 == 0:
+            seqs.insert(3, "")
+        for B in (1, 2, 5, 64, -1):
+            st = _flat_equals_blocked(oracle, seqs, B)
+            recomputed += st["recomputed_blocks"]
+            kept += st["kept_rows"]
+    unit = "ACGGT"
+    rep = ["TTGACC" + unit * k + "GGATCA" for k in (6, 9, 6, 12, 9, 7)]
+    for B in (1, 4, 9):
+        _flat_equals_blocked(oracle, rep, B)
+    assert recomputed > 0 and kept > 0
+
+
+def test_full_size_configs2_golden_is_self_consistent(golden_dir):
+    """tests/golden/c3_full.json (oracle/gen_golden_c3.py: the row-checkpoint engine on configs[2] at FULL size)
+    names the window the GPU test aligns; the digest fields are present."""
+    path = os.path.join(golden_dir, "c3_full.json")
+    if not os.path.exists(path):
+        pytest.skip("c3_full.json not generated")
+    g = json.load(open(path))
+    from svscope_b200 import synth
+    import hashlib
+    w = synth.make_c3(seed=g["seed"])
+    assert len(w[0]) == g["n_seqs"]
+    assert hashlib.sha256("\n".join(w[0]).encode()).hexdigest() == g["input_sha256"]
+    assert len(g["msa_sha256"]) == 64 and len(g["consensus_sha256"]) == 64 and g["msa_cols"] > 20_000
