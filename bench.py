@@ -271,11 +271,15 @@ def cpu_baseline(windows, poa_cells_per_window, ed_cells_per_window, budget_s, w
               f"CPU time of a window) not charged")
     return dict(value=value_ed if with_ed else value_no_ed, unit=UNIT, cores=r["cores"], kind="port", sample=sample,
                 value_without_edit_distance=value_no_ed, value_with_edit_distance=value_ed,
+                value_reference_pool6=min(6, r["cores"]) / (t_with_ed if with_ed else t_window),
+                value_one_core=1.0 / (t_with_ed if with_ed else t_window),
                 poa_gcups_per_core=r["poa_cells_per_core_s"] / 1e9, ed_gcups_per_core=r["ed_cells_per_core_s"] / 1e9,
                 poa_cells_per_window=poa_cells_per_window, ed_cells_per_window=ed_cells_per_window, wall_s=r["wall_s"],
                 note="CPU restatement of pyspoa (scalar; the real pyspoa 0.2.1 SIMD engine cannot be installed offline and would "
                      "be several times faster) + bit-parallel Levenshtein; the reference itself runs no Levenshtein "
-                     "(src/DecisionMaker.py:76-84 is commented out): value_without_edit_distance is the reference-faithful path")
+                     "(src/DecisionMaker.py:76-84 is commented out): value_without_edit_distance is the reference-faithful path; "
+                     "value_reference_pool6 = the same rates on min(6, cores) processes, the pool size the reference itself "
+                     "uses (src/SVscope.py:158-161)")
 
 
 # ------------------------------------------------------------------------------------------
@@ -331,6 +335,15 @@ def main():
     for _ in range(max(args.warmup, 1)):
         run(slice_w, slice_reads)
     t_w = time.perf_counter() - t_w
+    # the edit-distance kernel alone on the same slice (in a step it runs beside the window kernels and its
+    # event time is that of a kernel sharing the SMs): the figure its own roofline fraction is quoted on
+    myers_alone = None
+    if ed:
+        from svscope_b200.batch import edit_distance_matrices
+        torch.cuda.synchronize()
+        sbase = np.concatenate([[0], np.cumsum([len(w[0]) for w in slice_w])])
+        _, myers_alone = edit_distance_matrices(ctx, slice_reads, [list(range(int(sbase[i]) + 1, int(sbase[i + 1])))
+                                                                   for i in range(len(slice_w))])
     slice_reads.close()
 
     # ---- per-step batch: the configs[1] batch, or its first n windows if K steps would not fit ------
@@ -479,12 +492,17 @@ def main():
                 "note": "algorithmic bytes = read + rank-ordered graph + alignment path (SURVEY 8d); implementation_bytes = "
                         "traceback codes written (1 B per evaluated cell of single-predecessor rows, 2 B otherwise)"}}
     ed_ms = max(st.get("ed_ms", 0.0), 1e-9)
+    myers_peak = alu["xor"] / 0.53
     kernels = {
-        "myers_kernel": {"bound": "int_alu", "achieved": st.get("ed_cells", 0.0) / ed_ms / 1e6, "unit": "GCUPS",
-                         "peak": alu["xor"] / 0.53, "frac": st.get("ed_cells", 0.0) / ed_ms / 1e6 / (alu["xor"] / 0.53),
+        "myers_kernel": {"bound": "int_alu", "unit": "GCUPS", "peak": myers_peak,
+                         "achieved": (myers_alone["cells"] / max(myers_alone["ms"], 1e-9) / 1e6) if myers_alone else None,
+                         "frac": (myers_alone["cells"] / max(myers_alone["ms"], 1e-9) / 1e6 / myers_peak) if myers_alone else None,
+                         "achieved_in_step": st.get("ed_cells", 0.0) / ed_ms / 1e6,
+                         "frac_in_step": st.get("ed_cells", 0.0) / ed_ms / 1e6 / myers_peak,
                          "note": "cells = L_i * L_j per pair; ~17 64-bit logic ops per 64-cell word step = 0.53 32-bit ops per cell "
-                                 "against the measured LOP3 issue rate; kernel time by CUDA events on its stream, which it "
-                                 "shares with the tail of the window kernels (it runs behind them)"},
+                                 "against the measured LOP3 issue rate; achieved / frac: the kernel ALONE on the device (all read "
+                                 "pairs of the 64 warm-up windows, CUDA events on its stream); *_in_step: its event time inside a "
+                                 "step, where it shares the SMs with the window kernels (not a kernel rate)"},
         "em_kernel": {"bound": "latency", "note": "FP64, one CTA per (window, K): < 2 % of a step, occupancy/latency bound; "
                                                   "no roofline fraction claimed"}}
     cyc = {k: st.get("poa_cyc_" + k, 0.0) for k in ("export", "dp", "traceback", "merge", "rank", "finish")}
@@ -580,7 +598,8 @@ def main_reference(args):
             "run": {"sample_note": "one bounded sample, timed once (the driver's steps/warmup are echoed, not repeated); "
                                    "cells per window from the growth model of bench.model_cells x (1 + consensus share)"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "value_without_edit_distance",
-                                                "value_with_edit_distance", "poa_gcups_per_core", "ed_gcups_per_core")},
+                                                "value_with_edit_distance", "value_reference_pool6", "value_one_core",
+                                                "poa_gcups_per_core", "ed_gcups_per_core")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "reference = negi2331026/SVScope Python path; its spoa.poa lives in the pyspoa wheel that cannot be "

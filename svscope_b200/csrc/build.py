@@ -43,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             subprocess.run(cmd, check=True)
             changed = True
     if changed or not os.path.exists(LIB):
-        cmd = ["nvcc", "-shared", "-o", LIB] + objs + ["-lcudart", "-lpthread"]
+        cmd = ["nvcc", "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB] + objs + ["-lcudart", "-lpthread"]
         subprocess.run(cmd, check=True)
     return LIB
 

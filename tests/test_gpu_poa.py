@@ -219,30 +219,25 @@ def test_window_with_more_than_31_in_edges_fails_alone(ctx, oracle):
     reads.close()
 
 
-def test_full_size_deep_tandem_repeat_window_properties(ctx):
+def test_full_size_deep_tandem_repeat_window_properties(ctx, c3_full_gpu):
     """configs[2] at FULL size (120 reads of 20 kb, 10 % error, tandem-repeat expansion): the graph
-    outgrows the tier-0 scratch slots, so this exercises the memory tiers; the CPU oracle cannot hold
-    five 200k x 20k matrices, so parity is checked through size-independent properties: every MSA
-    row spells its read, the rows are equally long, the consensus is a path of plausible length,
-    and a second CTA shape gives the identical result (the scaled-down window against the oracle is
-    test_full_size_windows_equal_oracle_golden)."""
-    if os.environ.get("SVS_SKIP_FULL_C3"):
-        pytest.skip("SVS_SKIP_FULL_C3 set")
+    outgrows the tier-0 scratch slots, so this exercises the memory tiers.  Size-independent properties:
+    every MSA row spells its read, the rows are equally long, the consensus is a path of plausible length,
+    and a second CTA shape gives the identical result.  The comparison with the CPU oracle (row-checkpoint
+    engine, committed digests) is tests/test_zz_gpu_full_c3_golden.py; the scaled-down window against the
+    flat oracle is test_full_size_windows_equal_oracle_golden."""
     from svscope_b200._lib import ReadSet
     from svscope_b200.poa_api import poa_groups
-    w = synth.make_c3(seed=3)
-    seqs = w[0]
+    seqs, cons, msas, st = (c3_full_gpu[k] for k in ("seqs", "cons", "msas", "st"))
     assert len(seqs) == 121 and min(len(s) for s in seqs[1:]) > 15_000
+    assert st["failed_groups"] == 0
+    msa = msas[0]
+    assert len(msa) == len(seqs) and len({len(r) for r in msa}) == 1
+    assert [r.replace("-", "") for r in msa] == seqs
+    assert 0.8 * len(seqs[0]) < len(cons[0]) < 1.6 * len(seqs[0])
     reads = ReadSet(ctx, seqs)
     try:
         ctx.set_option("poa_threads", 512)
-        cons, msas, st = poa_groups(ctx, reads, [list(range(len(seqs)))])
-        assert st["failed_groups"] == 0
-        msa = msas[0]
-        assert len(msa) == len(seqs) and len({len(r) for r in msa}) == 1
-        assert [r.replace("-", "") for r in msa] == seqs
-        assert 0.8 * len(seqs[0]) < len(cons[0]) < 1.6 * len(seqs[0])
-        ctx.set_option("poa_threads", 384)
         cons2, msas2, _ = poa_groups(ctx, reads, [list(range(len(seqs)))])
         assert cons2 == cons and msas2 == msas
     finally:
