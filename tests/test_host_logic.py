@@ -570,3 +570,37 @@ def test_cell_header_table_keys_and_codes_selfcheck():
     from tests.emul.emul import cell_selfcheck
     bad, n = cell_selfcheck(seed=7, n_random=300)
     assert n > 100000 and bad == 0
+
+
+def test_bench_line_contract_with_device_stand_ins():
+    """bench.py's control flow and JSON line with stand-ins for the device stages (tests/tools/fake_bench.py):
+    the keys the driver reads, the per-step batch shrinking to the time budget (with the second calibration
+    step), and `config` being the identical dict in the ours arm and in --impl reference."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fake = os.path.join(root, "tests", "tools", "fake_bench.py")
+    out = subprocess.run([sys.executable, fake, "0.005", "--windows", "200", "--steps", "6", "--warmup", "3", "--budget-s", "3",
+                          "--total-s", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["steps"] == 6 and line["warmup"] == 3 and line["n_gpus"] == 1 and line["scaling"] == "weak"
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert "model" not in line["config"] and line["config"]["workload"].startswith("configs[1]")
+    # 6 steps of the full batch (1 s each with the stand-ins) do not fit 3 s: the step shrinks, and says so
+    assert 64 <= line["run"]["windows_per_step"] < 200
+    assert line["calibration"]["second_calibration_windows"] >= line["run"]["windows_per_step"]
+    assert line["ms_per_step"] * 6 / 1e3 < 3.0 * 1.35
+    ref = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--cpu-budget", "0.5",
+                          "--windows", "200", "--steps", "6", "--warmup", "3"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert ref.returncode == 0, ref.stderr[-2000:]
+    rline = json.loads(ref.stdout.strip().splitlines()[-1])
+    assert rline["impl"] == "reference" and rline["config"] == line["config"]
+    assert rline["metric"] == line["metric"] and rline["unit"] == line["unit"]
+    assert rline["e2e"]["h2d_bytes_per_step"] == 0 and rline["cpu_baseline"]["kind"] == "port"
