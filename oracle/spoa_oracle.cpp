@@ -13,6 +13,10 @@
 // Tie-break precedence, node-id order, in-edge order and the DFS visiting order are the
 // parts kernels must reproduce, so they are kept in ONE place here.
 //
+// Two engines share the graph code and ONE traceback (trace_back): the flat five-matrix engine (Engine) and a
+// bounded-memory row-checkpoint engine (BlockedEngine, spo_set_blocked) for windows whose matrices do not fit
+// in memory; tests/test_oracle_golden.py holds them equal, read after read.
+//
 // Build: see oracle/Makefile (g++ -O3 -shared -fPIC).  Interface: plain C, used via ctypes
 // from oracle/oracle.py.
 

@@ -65,8 +65,8 @@ def EMCluster(seqdatamx, initselection=1, max_C=9, ShowPlot=False):
     """Cluster reads with the categorical mixture model; reference :221-277."""
     if initselection != 1:
         raise NotImplementedError("only initselection=1 (hierarchical initialisation) is on the path")
-    if max_C != 9:
-        raise NotImplementedError("max_C is fixed to 9 on the accelerated path")
+    if not 2 <= int(max_C) <= _batch.MAX_C:
+        raise NotImplementedError("max_C from 2 to 9 (the mixture kernel is built for K <= 9; the reference passes 9)")
     ctx = Context.default()
     X = np.asarray(seqdatamx)
     nf = X.shape[1]
@@ -74,5 +74,5 @@ def EMCluster(seqdatamx, initselection=1, max_C=9, ShowPlot=False):
     sim = ident.astype(np.float64) / (nf if nf else 1)
     np.fill_diagonal(sim, 1.0)
     # no per-call reseed here: like the reference, EMCluster draws from the process-wide RNG
-    fit = _batch.em_cluster_many(ctx, [X], [sim], [zp], want_theta=True, reseed=False)[0]
+    fit = _batch.em_cluster_many(ctx, [X], [sim], [zp], want_theta=True, reseed=False, max_C=int(max_C))[0]
     return [fit["K"], seqdatamx, fit["labels"], fit["theta"], fit["gamma"], fit["pi"], fit["bics"]]

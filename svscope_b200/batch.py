@@ -251,8 +251,9 @@ def _resume_fit(ctx, X, K, labels, first, want_theta):
 
 
 def em_cluster_many(ctx: Context, Xs: List[np.ndarray], sims: List[np.ndarray], zero_params: List[int],
-                    want_theta: bool = False, reseed: bool = True):
-    """EMCluster for every X in ``Xs`` (features already selected, similarity matrices given).
+                    want_theta: bool = False, reseed: bool = True, max_C: int = 0):
+    """EMCluster for every X in ``Xs`` (features already selected, similarity matrices given);
+    ``max_C`` = largest K tried (reference default 9 = the kernel's largest K; 0: that default).
 
     Returns per window dict(K, labels, gamma, pi, theta, bics, n_redraws)."""
     from scipy.cluster.hierarchy import fcluster, linkage
@@ -261,7 +262,7 @@ def em_cluster_many(ctx: Context, Xs: List[np.ndarray], sims: List[np.ndarray], 
     for w, (X, sim) in enumerate(zip(Xs, sims)):
         Z = linkage(sim, "ward")                                           # ReadsCluster.py:243
         trees.append(Z)
-        for K in range(1, int(np.min([MAX_C + 1, X.shape[0]]))):           # :238, :246
+        for K in range(1, int(np.min([(max_C or MAX_C) + 1, X.shape[0]]))):  # :238, :246
             labels = fcluster(Z, K, criterion="maxclust") - 1             # :94-97
             tasks.append(EmTaskSpec(w, K, labels.astype(np.int32)))
             owner.append(w)

@@ -437,9 +437,10 @@ def test_em_host_driver_replays_the_reference_rng_order(oracle, monkeypatch):
             noise = rng.random((N, nf)) < float(rng.choice([0.0, 0.05, 0.3]))
             X[noise] = rng.integers(0, 5, int(noise.sum()))
             X = X.astype(np.int64)
-            want, info = oracle.em_cluster(X, reseed=True, return_info=True)
+            max_C = 9 if it % 3 else int(rng.integers(2, 9))       # EMCluster's max_C (the reference passes the default)
+            want, info = oracle.em_cluster(X, max_C=max_C, reseed=True, return_info=True)
             got = batch.em_cluster_many(None, [X], [oracle.pairwise_identity(X)], [oracle.zero_param_num(X)],
-                                        want_theta=True, reseed=True)[0]
+                                        want_theta=True, reseed=True, max_C=max_C)[0]
             assert got["K"] == want[0] and np.array_equal(got["labels"], want[2]), it
             assert np.allclose(got["bics"], want[6], rtol=1e-9, equal_nan=True)
             assert np.allclose(got["gamma"], want[4], rtol=1e-9, atol=1e-300) and np.allclose(got["pi"], want[5], rtol=1e-9)
