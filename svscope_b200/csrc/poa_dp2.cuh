@@ -572,12 +572,19 @@ __device__ __forceinline__ void dp2_align(const PoaTask& tk, const Scores& s, co
         }
         DP_MARK(6);
       }
-      // rows at the end of the batch that were skipped: tell the consumer
-      if (i0 + nrows > R) {   // end of the pass: everything is stored
-        if (unfenced) { __threadfence_block(); unfenced = false; }
-        if (lane == 31) fprog[warp] = pbase_prog + static_cast<int>(R);
+      // End of the batch: rows at its end that were skipped count as done, and everything the warp stored in
+      // the batch is fenced and published in fprog as well.  Without this a warp that visits no row for more
+      // than 32 rows after an exported row p (a pruned or far-away branch in between) would wait for its right
+      // neighbour before its next fence, while that neighbour waits for the fence of p (dp2_stage_global): a
+      // cyclic wait.  With it fprog[w] >= the end of warp w's last finished batch; when warp w waits for warp
+      // w + 1 (more than 32 rows behind), w + 1 stands in an earlier batch (batch boundaries depend on the graph
+      // only), so every row it can ask for is fenced.
+      if (unfenced) { __threadfence_block(); unfenced = false; }
+      __syncwarp();
+      if (lane == 31) {
+        fprog[warp] = pbase_prog + static_cast<int>(i0 + nrows - 1);
+        prog[warp] = pbase_prog + static_cast<int>(i0 + nrows - 1);
       }
-      if (lane == 31) prog[warp] = pbase_prog + static_cast<int>(i0 + nrows - 1);
       i0 += nrows;
     }
     if (owns_end) {

@@ -5,6 +5,13 @@
 // poa_kernels.cu around the DP (task set-up, pruning attempts).  Not shipped.
 #include "cuda_shim.h"
 
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <thread>
+#include <unistd.h>
+
 #include "../../svscope_b200/csrc/poa_cell.h"
 #include "../../svscope_b200/csrc/poa_task.h"
 #include "poa_graph.h"
@@ -68,6 +75,32 @@ int run(const RankedGraph& G, const Scores& s, const uint8_t* read, uint32_t L, 
   tk.lb_guess = lb_guess;
   int n_retries = 0, rc = 0;
   CtaExec x;
+  // debugging aid: SVS_EMU_WATCHDOG=<seconds> prints the progress words of every warp if the CTA has not finished by then
+  std::atomic<bool> cta_done{false};
+  std::thread watchdog;
+  if (const char* wd = getenv("SVS_EMU_WATCHDOG")) {
+    const double limit = atof(wd);
+    watchdog = std::thread([&, limit]() {
+      for (double t = 0; t < limit && !cta_done.load(); t += 0.05) std::this_thread::sleep_for(std::chrono::milliseconds(50));
+      if (cta_done.load()) return;
+      const int NW = T / 32;
+      const volatile int* prog = reinterpret_cast<const volatile int*>(smem + static_cast<size_t>(T) * 32 * (ring_rows + 2) +
+                                                                       static_cast<size_t>(NW) * kCarryDepth * sizeof(Carry));
+      fprintf(stderr, "dp2 watchdog: R %u L %u npass %u strip %u ring %d prune %u\n", tk.R, tk.L, tk.npass, tk.strip, ring_rows, tk.prune);
+      for (int w = 0; w < NW; ++w) fprintf(stderr, "  warp %d prog %d fprog %d\n", w, prog[w], prog[16 + w]);
+      for (int w = 0; w < NW; ++w) {
+        const uint32_t i = static_cast<uint32_t>(prog[w]) % (tk.R + 1);
+        for (uint32_t r = (i > 4 ? i - 4 : 1); r <= std::min(tk.R, i + 40); ++r) {
+          fprintf(stderr, "  row %u band [%d,%d] chunks [%d,%d] preds", r, band[2 * r], band[2 * r + 1], (band[2 * r] - 1) >> 3, (band[2 * r + 1] - 1) >> 3);
+          for (uint32_t e = tk.pred_off[r]; e < tk.pred_off[r + 1]; ++e) fprintf(stderr, " %u", tk.preds[e]);
+          fprintf(stderr, "%s\n", (tk.flags[r] & kFlagExport) ? " export" : "");
+        }
+        fprintf(stderr, "  --\n");
+      }
+      fflush(stderr);
+      _exit(4);
+    });
+  }
   shim_run_cta(T, [&](int tid) {
     // poa_kernels.cu: bands (pruned: from the guessed lower bound; else full rows), exact-size code rows;
     // a result below the guess repeats the alignment with the score found
@@ -91,6 +124,8 @@ int run(const RankedGraph& G, const Scores& s, const uint8_t* read, uint32_t L, 
     if (tid < 32) tb3_walk_warp(tk, s, tbrows);
     __syncthreads();
   });
+  cta_done.store(true);
+  if (watchdog.joinable()) watchdog.join();
   if (rc != 0) return rc;
   if (tk.result[2] < 0 || tk.result[0] <= 0) return -1;
   rev_pairs->assign(tk.path, tk.path + 2 * static_cast<size_t>(tk.result[2]));

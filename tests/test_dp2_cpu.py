@@ -60,3 +60,30 @@ def test_dp2_source_on_cpu_adversarial_groups(oracle):
             seqs[3] = synth._to_str(synth._rand_seq(rng, 900))       # unrelated read
         retries += _check_group(oracle, seqs, ring_rows=int(rng.integers(1, 4)), warp_threads=128, warp_prune=1)
     assert retries >= 1      # the retry path ran
+
+
+def test_dp2_source_on_cpu_no_cyclic_wait_after_an_exported_row(golden_dir):
+    """Regression (found by tests/tools/fuzz_dp2_cpu.py, seed 11): warp 3 asked for the fence of an exported row of
+    warp 2 (dp2_stage_global) while warp 2, whose next row with cells came 40 pruned rows later, waited for warp 3
+    to come within 32 rows - fences were only issued every 8 visited rows.  The end-of-batch fence in poa_dp2.cuh
+    breaks the cycle.  Run in a child process: a cyclic wait would otherwise hang the suite."""
+    import json
+    import os
+    import subprocess
+    import sys
+    case = os.path.join(golden_dir, "dp2_deadlock_case.json")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import json, sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from oracle import oracle as O\n"
+        "from tests.emul.emul import EmuSession\n"
+        "d = json.load(open(%r))\n"
+        "for kw in (d['kw'], dict(d['kw'], warp_threads=256), dict(d['kw'], ring_rows=1)):\n"
+        "    o, e = O.PoaSession(1), EmuSession(**kw)\n"
+        "    for s in d['seqs']:\n"
+        "        assert np.array_equal(o.add(s), e.add(s))\n"
+        "print('ok')\n" % (root, case))
+    env = dict(os.environ, SVS_EMU_WATCHDOG="90")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=400, env=env)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), (out.returncode, out.stderr[-1500:])

@@ -3,6 +3,11 @@ OS thread per warp and one context per lane) against the five-matrix oracle: the
 fuzz_emul.py scaled up so that alignments span several strips, all CTA shapes, ring depths 1-8, pruning on/off.
 
     python tests/tools/fuzz_dp2_cpu.py --seconds 600 --seed 1
+    SVS_EMU_WATCHDOG=120 python tests/tools/fuzz_dp2_cpu.py --seconds 600 --seed 1 --last-group /tmp/last.json
+
+With SVS_EMU_WATCHDOG=<seconds> an emulated CTA that has not finished by then (a cyclic wait between warps) prints the
+progress words of its warps and exits with code 4 (tests/emul/dp2_threads.cpp); --last-group keeps the group that was
+running.  This is how the hand-over deadlock fixed in poa_dp2.cuh (end-of-batch fence) was found.
 """
 import argparse
 import os
@@ -48,6 +53,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=60)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--last-group", default="", help="file that always holds the group being run (json)")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     t0 = time.time()
@@ -58,6 +64,10 @@ def main():
         threads = int(rng.choice([128, 128, 256, 384, 512]))
         ring = int(rng.integers(1, 9))
         kw = dict(ring_rows=ring, warp_threads=threads, warp_prune=int(rng.random() < 0.7))
+        if args.last_group:
+            import json
+            with open(args.last_group, "w") as f:
+                json.dump(dict(seed=args.seed, group=n, kw=kw, seqs=seqs), f)
         o, e = O.PoaSession(1), EmuSession(**kw)
         for k, s in enumerate(seqs):
             a, b = o.add(s), e.add(s)
