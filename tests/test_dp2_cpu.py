@@ -31,6 +31,7 @@ def _check_group(oracle, seqs, **kw):
     (128, 3, 2400, 500, 4, 1),     # three strips, bands
     (256, 8, 2600, 700, 3, 1),     # 256 threads, two strips
     (256, 4, 1500, 300, 3, 0),     # unpruned, one strip of six warps
+    (384, 8, 3300, 600, 3, 1),     # the product's default shape (twelve warps, ring of 8 rows), two strips, bands
 ])
 def test_dp2_source_on_cpu_equals_oracle(oracle, threads, ring, body, sv, nreads, prune):
     w = synth.make_sv_window(100 + body + threads, body, "DEL" if body % 200 else "INS", sv, nreads, nreads,

@@ -1,6 +1,6 @@
 """Offline fuzzing of the product's DP kernel SOURCE on the CPU (tests/emul/cuda_shim.h: poa_dp2.cuh run by one
 OS thread per warp and one context per lane) against the five-matrix oracle: the adversarial groups of
-fuzz_emul.py scaled up so that alignments span several strips, all CTA shapes, ring depths 1-8, pruning on/off.
+fuzz_emul.py scaled up so that alignments span several strips, tandem-repeat expansions, all CTA shapes, ring depths 1-8, pruning on/off.
 
     python tests/tools/fuzz_dp2_cpu.py --seconds 600 --seed 1
     SVS_EMU_WATCHDOG=120 python tests/tools/fuzz_dp2_cpu.py --seconds 600 --seed 1 --last-group /tmp/last.json
@@ -49,6 +49,20 @@ def make_long_group(rng):
     return seqs
 
 
+def make_repeat_group(rng):
+    """Tandem-repeat expansion: motif of 9-60 bases, reads with different copy numbers (edges that enter a long
+    branch late, branches the pruning removes), 3-10 % error - the shape that produced the cyclic wait of seed 11."""
+    motif = rand_seq(rng, int(rng.integers(9, 60)))
+    f5, f3 = rand_seq(rng, int(rng.integers(100, 700))), rand_seq(rng, int(rng.integers(100, 500)))
+    copies = int(rng.integers(2, 12))
+    seqs = []
+    for _ in range(int(rng.integers(4, 9))):
+        e = float(rng.choice([0.03, 0.05, 0.1]))
+        s = f5 + motif * (copies + int(rng.choice([0, 0, 1, 2, 3, 5, 8]))) + f3
+        seqs.append(mutate(rng, s, e * 0.4, e * 0.3, e * 0.3))
+    return seqs
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=60)
@@ -59,8 +73,9 @@ def main():
     t0 = time.time()
     n = n_long = retries = 0
     while time.time() - t0 < args.seconds:
-        long_group = rng.random() < 0.5
-        seqs = make_long_group(rng) if long_group else make_group(rng)
+        kind = rng.random()
+        long_group = kind < 0.5
+        seqs = make_long_group(rng) if kind < 0.4 else make_repeat_group(rng) if kind < 0.5 else make_group(rng)
         threads = int(rng.choice([128, 128, 256, 384, 512]))
         ring = int(rng.integers(1, 9))
         kw = dict(ring_rows=ring, warp_threads=threads, warp_prune=int(rng.random() < 0.7))
