@@ -67,6 +67,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=60)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--threads", type=int, default=0, help="CTA size (0: drawn from 128 / 256 / 384 / 512)")
+    ap.add_argument("--ring", type=int, default=0, help="ring depth (0: drawn from 1..8)")
     ap.add_argument("--last-group", default="", help="file that always holds the group being run (json)")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
@@ -78,6 +80,7 @@ def main():
         seqs = make_long_group(rng) if kind < 0.4 else make_repeat_group(rng) if kind < 0.5 else make_group(rng)
         threads = int(rng.choice([128, 128, 256, 384, 512]))
         ring = int(rng.integers(1, 9))
+        threads, ring = args.threads or threads, args.ring or ring
         kw = dict(ring_rows=ring, warp_threads=threads, warp_prune=int(rng.random() < 0.7))
         if args.last_group:
             import json
